@@ -1,0 +1,701 @@
+// conv_umma.cu - tcgen05 implicit-GEMM convolution for sm_100a.
+//
+// The contraction of every Conv2D whose C_in is a multiple of 64 (all ResNet / VGG convs but the
+// RGB stem).  GEMM view: M = output pixels, N = C_out, K = taps x C_in.
+//
+//   * A (activations, NHWC bf16 planes) is never im2col'ed: for tap (kh, kw) the 128-row A tile is a
+//     4-D TMA box {64 channels, tile_w, tile_h, tile_n} of the input tensor shifted by (kh-pad, kw-pad);
+//     TMA zero-fills out-of-bounds elements, which IS the 'same' / ZeroPadding2D border, and its
+//     element strides do stride-2 sub-sampling.  1x1/stride-1 convs use the flat [M, C] view.
+//   * B (weights) is pre-arranged once as [tap][C_out][C_in] bf16 (K-major), a 3-D TMA box.
+//   * Both land in 128B-swizzled shared memory and feed tcgen05.mma (M=128, N=BN, K=16) issued by
+//     one thread; the fp32 accumulator lives in TMEM.
+//   * BF16X2 format (fp32 parity path): activations and weights are (hi, lo) bf16 planes and each
+//     K step issues hi*hi + lo*hi + hi*lo  (bf16x3, ~2^-16 relative) into the same accumulator.
+//   * Epilogue (4 warps): tcgen05.ld -> per-channel scale/shift (bias + BN) -> + residual -> relu ->
+//     re-split to bf16 planes -> global stores (plain st.global, so the output may be a peer GPU's
+//     input slot: the hop is fused into the kernel).
+//   * Optional split-K over grid.z for weight-heavy small-M layers (7x7, 14x14 maps at batch 1):
+//     partial tiles go to an fp32 workspace; the last CTA of a tile reduces them in a fixed order.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace defer {
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 64;           // K elements per stage (128 B of bf16 = one swizzle atom row)
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+struct KParams {
+  // geometry
+  int n, ho, wo, cout;
+  int tile_n, tile_h, tile_w, tiles_h, tiles_w;   // M tile = tile_n x tile_h x tile_w output pixels
+  int flat;                                       // flat [M, C] view: rows = consecutive pixels
+  int m_total;                                    // n*ho*wo
+  int kh, kw, sh, sw, pad_t, pad_l;
+  int cblocks;                                    // cin / 64
+  int k_blocks;                                   // taps * cblocks
+  int splits;
+  uint32_t flags;
+  const float* scale;
+  const float* shift;
+  const void* res;
+  void* y;
+  float* partial;
+  unsigned int* counters;
+  size_t plane_out;                               // n*ho*wo*cout (elements) - offset of the lo plane
+  int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = gtimer();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfff) == 0 && gtimer() - t0 > 2000000000ull) {
+      if (error_flag) atomicExch(error_flag, 100 + tag);
+      printf("conv_umma: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SWIZZLE_128B, K-major smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 |
+// SBO(=1024 B >> 4)<<32 | version(=1)<<46 | layout_type(=2, SWIZZLE_128B)<<61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// K-major A and B (bits 15, 16 = 0), N>>3 at bit 17, M>>4 at bit 24
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int NPLANES, int BN>
+struct SmemLayout {
+  static constexpr int A_PLANE = BM * 128;          // bytes
+  static constexpr int B_PLANE = BN * 128;
+  static constexpr int STAGE = NPLANES * (A_PLANE + B_PLANE);
+  static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
+  static constexpr int BAR_OFF = STAGES * STAGE;    // full[STAGES], empty[STAGES], tmem_full, tmem slot
+  static constexpr int SCALE_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = SCALE_OFF + 2 * BN * 4 + 1024;  // + slack for the 1024-B alignment
+};
+
+// ---------------------------------------------------------------------------------------------- the kernel
+template <int NPLANES, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
+                 const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, const KParams p) {
+  using L = SmemLayout<NPLANES, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * L::STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (2 * L::STAGES + 1));
+  float* s_scale = reinterpret_cast<float*>(smem + L::SCALE_OFF);
+  float* s_shift = s_scale + BN;
+  __shared__ int s_is_last;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tile_id = blockIdx.x;
+  int n0 = 0, h0 = 0, w0 = 0;
+  if (p.flat) {
+    w0 = tile_id * BM;
+  } else {
+    int tw = tile_id % p.tiles_w;
+    int t2 = tile_id / p.tiles_w;
+    int th = t2 % p.tiles_h;
+    int tn = t2 / p.tiles_h;
+    n0 = tn * p.tile_n;
+    h0 = th * p.tile_h;
+    w0 = tw * p.tile_w;
+  }
+  const int c_base = blockIdx.y * BN;
+  // split-K range
+  const int split = blockIdx.z;
+  const int kb_per = (p.k_blocks + p.splits - 1) / p.splits;
+  const int kb_begin = split * kb_per;
+  const int kb_end = min(p.k_blocks, kb_begin + kb_per);
+  const int num_kb = kb_end - kb_begin;   // host guarantees >= 1
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmx0);
+    prefetch_tmap(&tmw0);
+    if (NPLANES == 2) {
+      prefetch_tmap(&tmx1);
+      prefetch_tmap(&tmw1);
+    }
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    constexpr uint32_t ncols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+      int c = c_base + i;
+      s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
+      s_shift[i] = (p.shift && c < p.cout) ? p.shift[c] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =================================================================== TMA producer
+    if (lane == 0) {
+      constexpr uint32_t stage_bytes = NPLANES * (L::A_PLANE + L::B_PLANE);
+      // bytes TMA actually delivers: the full boxes (OOB elements are zero-filled and still counted)
+      const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
+      const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
+      (void)stage_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1, p.error_flag, 1);
+        const int tap = kb / p.cblocks;
+        const int cb = kb - tap * p.cblocks;
+        const int khi = tap / p.kw;
+        const int kwi = tap - khi * p.kw;
+        const uint32_t a_dst = smem_base + stage * L::STAGE;
+        const uint32_t b_dst = a_dst + NPLANES * L::A_PLANE;
+        mbar_expect_tx(full_bar(stage), tx_bytes);
+        int cw, ch, cn;
+        if (p.flat) {
+          cw = w0; ch = 0; cn = 0;
+        } else {
+          cw = w0 * p.sw + kwi - p.pad_l;
+          ch = h0 * p.sh + khi - p.pad_t;
+          cn = n0;
+        }
+        tma_load_4d(a_dst, &tmx0, full_bar(stage), cb * BK, cw, ch, cn);
+        tma_load_3d(b_dst, &tmw0, full_bar(stage), cb * BK, c_base, tap);
+        if (NPLANES == 2) {
+          tma_load_4d(a_dst + L::A_PLANE, &tmx1, full_bar(stage), cb * BK, cw, ch, cn);
+          tma_load_3d(b_dst + L::B_PLANE, &tmw1, full_bar(stage), cb * BK, c_base, tap);
+        }
+        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(full_bar(stage), phase, p.error_flag, 2);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * L::STAGE;
+        const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
+          const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));
+          if (NPLANES == 2) {
+            const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
+            const uint64_t b_lo = make_sw128_desc(b_addr + L::B_PLANE + k * (UMMA_K * 2));
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, accum);   // small terms first
+            accum = 1;
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, accum);
+          }
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, accum);
+          accum = 1;
+        }
+        umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
+        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);          // accumulator complete
+    }
+  } else {
+    // =================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;           // accumulator row == tile-local pixel
+    // row -> output pixel
+    bool valid;
+    size_t pix;
+    if (p.flat) {
+      int m = w0 + r;
+      valid = m < p.m_total;
+      pix = (size_t)m;
+    } else {
+      int tw = r % p.tile_w;
+      int t2 = r / p.tile_w;
+      int th = t2 % p.tile_h;
+      int tn = t2 / p.tile_h;
+      int nn = n0 + tn, oh = h0 + th, ow = w0 + tw;
+      valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
+      pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
+    }
+    mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool relu = p.flags & DEFER_FLAG_RELU;
+
+    bool do_final = true;
+    if (p.splits > 1) {
+      // ---- split-K: publish the raw partial tile, the last CTA of this (tile, n-block) reduces
+      const size_t tile_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      float* mine = p.partial + ((tile_lin * p.splits + split) * BM + r) * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr_row + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          __stcg(reinterpret_cast<float4*>(mine + c0 + j),
+                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3])));
+      }
+      __threadfence();
+      epi_bar_sync();
+      if (threadIdx.x == 64) {
+        unsigned prev = atomicAdd(p.counters + tile_lin, 1u);
+        int last = (prev == (unsigned)(p.splits - 1));
+        if (last) p.counters[tile_lin] = 0;   // re-arm for the next launch
+        s_is_last = last;
+      }
+      epi_bar_sync();
+      do_final = s_is_last != 0;
+      if (do_final) __threadfence();
+    }
+
+    if (do_final) {
+      const size_t tile_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float acc[32];
+        if (p.splits > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          if (valid) {
+            for (int s = 0; s < p.splits; ++s) {
+              const float* src = p.partial + ((tile_lin * p.splits + s) * BM + r) * BN + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = __ldcg(reinterpret_cast<const float4*>(src + j));
+                acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+              }
+            }
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(taddr_row + c0, v);   // warp-collective: every lane takes part, stores are masked below
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        }
+        if (!valid) continue;
+        const int c = c_base + c0;
+        const size_t o = pix * p.cout + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], s_scale[c0 + j], s_shift[c0 + j]);
+        if (p.res) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + o;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 h = *reinterpret_cast<const uint4*>(rp + q * 8);
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[q * 8 + 2 * e] += __low2float(hh[e]);
+              acc[q * 8 + 2 * e + 1] += __high2float(hh[e]);
+            }
+            if (NPLANES == 2) {
+              uint4 l = *reinterpret_cast<const uint4*>(rp + p.plane_out + q * 8);
+              const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[q * 8 + 2 * e] += __low2float(ll[e]);
+                acc[q * 8 + 2 * e + 1] += __high2float(ll[e]);
+              }
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 h, l;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (NPLANES == 2) {
+              split_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1], hp[e], lp[e]);
+            } else {
+              hp[e] = pack_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+            }
+          }
+          *reinterpret_cast<uint4*>(yp + q * 8) = h;
+          if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + q * 8) = l;
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    constexpr uint32_t ncols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// weights: fp32 HWIO [tap][cin][cout]  ->  bf16 [plane][tap][cout][cin]
+__global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                               int taps, int cin, int cout, int nplanes) {
+  size_t total = (size_t)taps * cin * cout;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in the OUTPUT layout (coalesced writes)
+  if (i >= total) return;
+  int ci = (int)(i % cin);
+  size_t t2 = i / cin;
+  int co = (int)(t2 % cout);
+  int tap = (int)(t2 / cout);
+  float v = w[((size_t)tap * cin + ci) * cout + co];
+  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[i] = hi;
+  if (nplanes == 2) out[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, const uint32_t* estr) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DEFER_ERR_CUDA;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, (const cuuint64_t*)dims,
+                   (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, (const cuuint32_t*)estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return DEFER_ERR_CUDA;
+  }
+  return DEFER_OK;
+}
+
+template <int NPLANES, int BN>
+int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams& kp, cudaStream_t st) {
+  using L = SmemLayout<NPLANES, BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set[dev] = true;
+  }
+  dim3 grid(plan.tiles_n * plan.tiles_h * plan.tiles_w, plan.cout / BN, plan.splits);
+  conv_umma_kernel<NPLANES, BN><<<grid, NUM_THREADS, L::TOTAL, st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
+                                                                    plan.tmap_w[NPLANES - 1], kp);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- public
+bool umma_conv_supported(int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw, int sh, int sw,
+                         int pad_t, int pad_l) {
+  if (fmt != FMT_BF16X2 && fmt != FMT_BF16) return false;
+  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  if (sh < 1 || sw < 1 || sh > 2 || sw > 2) return false;
+  if (kh > 7 || kw > 7) return false;
+  if (n < 1 || ho < 1 || wo < 1 || h < 1 || w < 1) return false;
+  if ((size_t)n * ho * wo * cout >= (1ull << 40)) return false;
+  (void)pad_t; (void)pad_l;
+  return true;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
+                      int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
+                      const float* shift_dev) {
+  UmmaConvPlan& P = *plan;
+  P = UmmaConvPlan();
+  P.fmt = fmt;
+  P.nplanes = fmt == FMT_BF16X2 ? 2 : 1;
+  P.n = n; P.h = h; P.w = w; P.cin = cin; P.ho = ho; P.wo = wo; P.cout = cout;
+  P.kh = kh; P.kw = kw; P.sh = sh; P.sw = sw; P.pad_t = pad_t; P.pad_l = pad_l;
+  P.flags = flags;
+  P.scale = scale_dev;
+  P.shift = shift_dev;
+  const int taps = kh * kw;
+  P.k_blocks = taps * (cin / 64);
+
+  // ---- M tiling
+  P.flat = (kh == 1 && kw == 1 && sh == 1 && sw == 1 && pad_t == 0 && pad_l == 0) ? 1 : 0;
+  if (P.flat) {
+    long long m = (long long)n * ho * wo;
+    P.tile_n = 1; P.tile_h = 1; P.tile_w = BM;
+    P.tiles_n = 1; P.tiles_h = 1; P.tiles_w = (int)((m + BM - 1) / BM);
+  } else {
+    int parts_w = (wo + BM - 1) / BM;                 // split very wide rows evenly
+    P.tile_w = (wo + parts_w - 1) / parts_w;
+    P.tiles_w = (wo + P.tile_w - 1) / P.tile_w;
+    P.tile_h = BM / P.tile_w;
+    if (P.tile_h > ho) P.tile_h = ho;
+    // balance rows across tiles (e.g. 14 rows: 7+7 instead of 9+5)
+    P.tiles_h = (ho + P.tile_h - 1) / P.tile_h;
+    P.tile_h = (ho + P.tiles_h - 1) / P.tiles_h;
+    P.tile_n = 1;
+    if (P.tile_h == ho && P.tiles_w == 1) {
+      P.tile_n = BM / (P.tile_h * P.tile_w);
+      if (P.tile_n > n) P.tile_n = n;
+      if (P.tile_n < 1) P.tile_n = 1;
+    }
+    P.tiles_n = (n + P.tile_n - 1) / P.tile_n;
+    if (P.tile_w * sw > 256 || P.tile_h * sh > 256) {
+      set_error("umma conv: TMA box too large (tile %dx%d stride %dx%d)", P.tile_h, P.tile_w, sh, sw);
+      return DEFER_ERR_INVALID;
+    }
+  }
+  const int m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
+
+  // ---- N tile and split-K: aim for >= ~1 wave of 148 SMs without shredding K
+  P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= 148) ? 128 : 64;
+  int force_bn = env_int("DEFER_UMMA_BN", 0);
+  if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) P.bn = force_bn;
+  int ctas = m_tiles * (cout / P.bn);
+  P.splits = 1;
+  int want_split = env_int("DEFER_UMMA_SPLITK", 1);
+  if (want_split && ctas < 96 && P.k_blocks >= 8) {
+    int s = (148 + ctas - 1) / ctas;
+    int max_s = P.k_blocks / 4;          // keep >= 4 k-blocks (256 K elements) per split
+    if (s > max_s) s = max_s;
+    if (s > 32) s = 32;
+    if (s < 1) s = 1;
+    // make every split non-empty
+    int per = (P.k_blocks + s - 1) / s;
+    s = (P.k_blocks + per - 1) / per;
+    P.splits = s;
+  }
+  int force_split = env_int("DEFER_UMMA_FORCE_SPLITS", 0);
+  if (force_split > 0 && force_split <= P.k_blocks) {
+    int per = (P.k_blocks + force_split - 1) / force_split;
+    P.splits = (P.k_blocks + per - 1) / per;
+  }
+
+  // ---- weights: fp32 HWIO -> bf16 [plane][tap][cout][cin]
+  size_t welems = (size_t)taps * cin * cout;
+  DEFER_CUDA(cudaMalloc(&P.w_dev, welems * 2 * P.nplanes));
+  {
+    unsigned grid = (unsigned)((welems + 255) / 256);
+    weight_transform_kernel<<<grid, 256>>>(w_hwio_dev, (__nv_bfloat16*)P.w_dev, taps, cin, cout, P.nplanes);
+    DEFER_CUDA(cudaGetLastError());
+  }
+  for (int pl = 0; pl < P.nplanes; ++pl) {
+    uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)taps};
+    uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * cout * 2};
+    uint32_t box[3] = {64, (uint32_t)P.bn, 1};
+    uint32_t es[3] = {1, 1, 1};
+    DEFER_TRY(encode_map(&P.tmap_w[pl], (uint8_t*)P.w_dev + pl * welems * 2, 3, dims, strides, box, es));
+  }
+  if (P.nplanes == 1) P.tmap_w[1] = P.tmap_w[0];
+  P.ready = true;
+  return DEFER_OK;
+}
+
+int umma_conv_bind(const UmmaConvPlan& P, UmmaConvLaneArgs* a, const void* x, const void* res, void* y) {
+  if (!P.ready) {
+    set_error("umma_conv_bind: plan not prepared");
+    return DEFER_ERR_STATE;
+  }
+  size_t xelems = (size_t)P.n * P.h * P.w * P.cin;
+  for (int pl = 0; pl < P.nplanes; ++pl) {
+    uint8_t* base = (uint8_t*)x + pl * xelems * 2;
+    if (P.flat) {
+      uint64_t m = (uint64_t)P.n * P.h * P.w;
+      uint64_t dims[4] = {(uint64_t)P.cin, m, 1, 1};
+      uint64_t strides[3] = {(uint64_t)P.cin * 2, m * P.cin * 2, m * P.cin * 2};
+      uint32_t box[4] = {64, BM, 1, 1};
+      uint32_t es[4] = {1, 1, 1, 1};
+      DEFER_TRY(encode_map(&a->tmap_x[pl], base, 4, dims, strides, box, es));
+    } else {
+      uint64_t dims[4] = {(uint64_t)P.cin, (uint64_t)P.w, (uint64_t)P.h, (uint64_t)P.n};
+      uint64_t strides[3] = {(uint64_t)P.cin * 2, (uint64_t)P.w * P.cin * 2, (uint64_t)P.h * P.w * P.cin * 2};
+      uint32_t box[4] = {64, (uint32_t)(P.tile_w * P.sw), (uint32_t)(P.tile_h * P.sh), (uint32_t)P.tile_n};
+      uint32_t es[4] = {1, (uint32_t)P.sw, (uint32_t)P.sh, 1};
+      DEFER_TRY(encode_map(&a->tmap_x[pl], base, 4, dims, strides, box, es));
+    }
+  }
+  if (P.nplanes == 1) a->tmap_x[1] = a->tmap_x[0];
+  a->res = res;
+  a->y = y;
+  a->partial = nullptr;
+  a->counters = nullptr;
+  if (P.splits > 1) {
+    size_t tiles = (size_t)P.tiles_n * P.tiles_h * P.tiles_w * (P.cout / P.bn);
+    DEFER_CUDA(cudaMalloc((void**)&a->partial, tiles * P.splits * BM * P.bn * sizeof(float)));
+    DEFER_CUDA(cudaMalloc((void**)&a->counters, tiles * sizeof(unsigned int)));
+    DEFER_CUDA(cudaMemset(a->counters, 0, tiles * sizeof(unsigned int)));
+  }
+  return DEFER_OK;
+}
+
+void umma_conv_unbind(UmmaConvLaneArgs* a) {
+  if (a->partial) cudaFree(a->partial);
+  if (a->counters) cudaFree(a->counters);
+  a->partial = nullptr;
+  a->counters = nullptr;
+}
+
+int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStream_t st) {
+  KParams kp;
+  kp.n = P.n; kp.ho = P.ho; kp.wo = P.wo; kp.cout = P.cout;
+  kp.tile_n = P.tile_n; kp.tile_h = P.tile_h; kp.tile_w = P.tile_w; kp.tiles_h = P.tiles_h; kp.tiles_w = P.tiles_w;
+  kp.flat = P.flat;
+  kp.m_total = P.n * P.ho * P.wo;
+  kp.kh = P.kh; kp.kw = P.kw; kp.sh = P.sh; kp.sw = P.sw; kp.pad_t = P.pad_t; kp.pad_l = P.pad_l;
+  kp.cblocks = P.cin / 64;
+  kp.k_blocks = P.k_blocks;
+  kp.splits = P.splits;
+  kp.flags = P.flags;
+  kp.scale = P.scale; kp.shift = P.shift;
+  kp.res = (P.flags & DEFER_FLAG_RESIDUAL) ? a.res : nullptr;
+  kp.y = a.y;
+  kp.partial = a.partial;
+  kp.counters = a.counters;
+  kp.plane_out = (size_t)P.n * P.ho * P.wo * P.cout;
+  kp.error_flag = nullptr;
+  if (P.nplanes == 2) return P.bn == 128 ? launch_t<2, 128>(P, a, kp, st) : launch_t<2, 64>(P, a, kp, st);
+  return P.bn == 128 ? launch_t<1, 128>(P, a, kp, st) : launch_t<1, 64>(P, a, kp, st);
+}
+
+void umma_conv_release(UmmaConvPlan& P) {
+  if (P.w_dev) cudaFree(P.w_dev);
+  P.w_dev = nullptr;
+  P.ready = false;
+}
+
+}  // namespace defer

@@ -1,0 +1,50 @@
+// conv_umma.cuh - interface of the tcgen05 implicit-GEMM convolution (conv_umma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace defer {
+
+// Shape-level plan: tiling, transformed weights (bf16 [tap][cout][cin], hi/lo planes), tensor map
+// for the weights.  Built once per op.
+struct UmmaConvPlan {
+  int fmt = 0, nplanes = 1;
+  int n = 0, h = 0, w = 0, cin = 0, ho = 0, wo = 0, cout = 0;
+  int kh = 1, kw = 1, sh = 1, sw = 1, pad_t = 0, pad_l = 0;
+  uint32_t flags = 0;
+  // M tile = box of (tile_n images) x (tile_h rows) x (tile_w cols) output pixels, <= 128 rows
+  int tile_n = 1, tile_h = 1, tile_w = 1, tiles_n = 1, tiles_h = 1, tiles_w = 1;
+  int flat = 0;            // 1: 1x1/stride-1 conv treated as a plain [M, K] GEMM (tile_w = 128 rows)
+  int bn = 64;             // N tile (cout per CTA)
+  int k_blocks = 0;        // taps * cin / 64
+  int splits = 1;          // split-K factor (grid.z)
+  int stages = 4;
+  size_t smem_bytes = 0;
+  void* w_dev = nullptr;   // transformed weights
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  CUtensorMap tmap_w[2];   // hi, lo
+  bool ready = false;
+};
+
+// Per-lane binding: tensor maps of the input activation planes + raw pointers for the epilogue.
+struct UmmaConvLaneArgs {
+  CUtensorMap tmap_x[2];
+  const void* res = nullptr;
+  void* y = nullptr;
+  float* partial = nullptr;          // split-K partial tiles (per lane: lanes run concurrently)
+  unsigned int* counters = nullptr;  // split-K arrival counters, one per output tile
+};
+
+bool umma_conv_supported(int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw, int sh, int sw,
+                         int pad_t, int pad_l);
+int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
+                      int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
+                      const float* shift_dev);
+int umma_conv_bind(const UmmaConvPlan& plan, UmmaConvLaneArgs* args, const void* x, const void* res, void* y);
+void umma_conv_unbind(UmmaConvLaneArgs* args);
+int launch_conv_umma(const UmmaConvPlan& plan, const UmmaConvLaneArgs& args, cudaStream_t st);
+void umma_conv_release(UmmaConvPlan& plan);
+
+}  // namespace defer

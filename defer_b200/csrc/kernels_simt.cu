@@ -1,0 +1,666 @@
+// kernels_simt.cu - SIMT kernels of the stage forward pass (sm_100a).
+//
+// These are the non-contraction ops of the reference's `model.predict` (src/node.py:105-106):
+// max-pool, global-average-pool, dense (HBM-bound GEMV at batch 1), softmax, standalone
+// BN/ReLU/Add/ZeroPad for arbitrary cut points, format encode/decode, and the device-side flag
+// kernels of the hop.  It also holds the exact-fp32 FFMA implicit-GEMM convolution that (a) serves
+// shapes the tcgen05 kernel does not take (C_in = 3 stem) and (b) is the in-library cross-check of
+// the tensor-core path.
+#include "common.cuh"
+
+namespace defer {
+
+// =============================================================================================
+// conv: implicit GEMM, fp32 FFMA.  M = n*ho*wo pixels, N = cout, K = kh*kw*cin.
+// 64x64 tile, BK = 16, 256 threads, 4x4 register tile per thread, register-prefetched.
+// =============================================================================================
+constexpr int CBM = 64, CBN = 64, CBK = 16;
+
+template <int FIN, int FOUT, bool VEC4>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
+  __shared__ __align__(16) float As[CBK][CBM + 4];
+  __shared__ __align__(16) float Bs[CBK][CBN + 4];
+
+  const int t = threadIdx.x;
+  const int M = p.n * p.ho * p.wo;
+  const int K = p.kh * p.kw * p.cin;
+  const int m0 = blockIdx.x * CBM;
+  const int n0 = blockIdx.y * CBN;
+  const size_t plane_in = (size_t)p.n * p.h * p.w_in * p.cin;
+  const size_t plane_out = (size_t)M * p.cout;
+
+  // A-load role: one pixel row, 4 consecutive k
+  const int ar = t >> 2;
+  const int akq = (t & 3) * 4;
+  const int am = m0 + ar;
+  const bool a_valid = am < M;
+  int a_nb = 0, a_ih0 = 0, a_iw0 = 0;
+  if (a_valid) {
+    int ow = am % p.wo;
+    int tmp = am / p.wo;
+    int oh = tmp % p.ho;
+    a_nb = tmp / p.ho;
+    a_ih0 = oh * p.sh - p.pad_t;
+    a_iw0 = ow * p.sw - p.pad_l;
+  }
+  // B-load role: one k row, 4 consecutive couts
+  const int bk = t >> 4;
+  const int bnq = (t & 15) * 4;
+  const bool b_vec = (p.cout % 4 == 0) && (n0 + bnq + 3 < p.cout);
+
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float a_reg[4];
+  float b_reg[4];
+
+  auto load_tile = [&](int k0) {
+    // ---- A
+    if constexpr (VEC4) {
+      int k = k0 + akq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_valid && k < K) {
+        int tap = k / p.cin;
+        int ci = k - tap * p.cin;
+        int khi = tap / p.kw;
+        int kwi = tap - khi * p.kw;
+        int ih = a_ih0 + khi, iw = a_iw0 + kwi;
+        if (ih >= 0 && ih < p.h && iw >= 0 && iw < p.w_in) {
+          size_t idx = (((size_t)a_nb * p.h + ih) * p.w_in + iw) * p.cin + ci;
+          v = act_load4<FIN>(p.x, plane_in, idx);
+        }
+      }
+      a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int k = k0 + akq + j;
+        float v = 0.f;
+        if (a_valid && k < K) {
+          int tap = k / p.cin;
+          int ci = k - tap * p.cin;
+          int khi = tap / p.kw;
+          int kwi = tap - khi * p.kw;
+          int ih = a_ih0 + khi, iw = a_iw0 + kwi;
+          if (ih >= 0 && ih < p.h && iw >= 0 && iw < p.w_in) {
+            size_t idx = (((size_t)a_nb * p.h + ih) * p.w_in + iw) * p.cin + ci;
+            v = act_load<FIN>(p.x, plane_in, idx);
+          }
+        }
+        a_reg[j] = v;
+      }
+    }
+    // ---- B
+    int k = k0 + bk;
+    if (k < K) {
+      const float* wp = p.w + (size_t)k * p.cout + n0 + bnq;
+      if (b_vec) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(wp));
+        b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b_reg[j] = (n0 + bnq + j < p.cout) ? __ldg(wp + j) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b_reg[j] = 0.f;
+    }
+  };
+
+  load_tile(0);
+  for (int k0 = 0; k0 < K; k0 += CBK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[akq + j][ar] = a_reg[j];
+    *reinterpret_cast<float4*>(&Bs[bk][bnq]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
+    __syncthreads();
+    if (k0 + CBK < K) load_tile(k0 + CBK);
+#pragma unroll
+    for (int k = 0; k < CBK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w};
+      float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: scale/shift (bias + BN folded), residual, relu, store in the stage format
+  const int c0 = n0 + tx * 4;
+  if (c0 >= p.cout) return;
+  const bool vec_out = (p.cout % 4 == 0) && (c0 + 3 < p.cout);
+  float sc[4], sf[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = c0 + j;
+    sc[j] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.f;
+    sf[j] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.f;
+  }
+  const bool relu = p.flags & DEFER_FLAG_RELU;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    size_t o = (size_t)m * p.cout + c0;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sf[j]);
+    if (vec_out) {
+      if (p.res) {
+        float4 r = act_load4<FOUT>(p.res, plane_out, o);
+        v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      act_store4<FOUT>(p.y, plane_out, o, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + j < p.cout) {
+          float u = v[j];
+          if (p.res) u += act_load<FOUT>(p.res, plane_out, o + j);
+          if (relu) u = fmaxf(u, 0.f);
+          act_store<FOUT>(p.y, plane_out, o + j, u);
+        }
+      }
+    }
+  }
+}
+
+template <int FIN, int FOUT>
+static int launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
+  int M = p.n * p.ho * p.wo;
+  dim3 grid((M + CBM - 1) / CBM, (p.cout + CBN - 1) / CBN);
+  if (p.cin % 4 == 0)
+    conv_simt_kernel<FIN, FOUT, true><<<grid, 256, 0, st>>>(p);
+  else
+    conv_simt_kernel<FIN, FOUT, false><<<grid, 256, 0, st>>>(p);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+int launch_conv_simt(int fmt, bool x_is_f32, const ConvParams& p, cudaStream_t st) {
+  switch (fmt) {
+    case FMT_F32: return launch_conv_simt_t<FMT_F32, FMT_F32>(p, st);
+    case FMT_BF16X2:
+      return x_is_f32 ? launch_conv_simt_t<FMT_F32, FMT_BF16X2>(p, st) : launch_conv_simt_t<FMT_BF16X2, FMT_BF16X2>(p, st);
+    case FMT_BF16:
+      return x_is_f32 ? launch_conv_simt_t<FMT_F32, FMT_BF16>(p, st) : launch_conv_simt_t<FMT_BF16, FMT_BF16>(p, st);
+  }
+  set_error("launch_conv_simt: bad fmt %d", fmt);
+  return DEFER_ERR_INVALID;
+}
+
+// =============================================================================================
+// max-pool with fused ZeroPadding2D (taps outside the tensor read 0.0, as Keras' explicit pad does)
+// one thread per (pixel, 4 channels)
+// =============================================================================================
+template <int FMT>
+__global__ void __launch_bounds__(256) maxpool_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h,
+                                                      int w, int c, int ph, int pw, int sh, int sw, int pad_t,
+                                                      int pad_l, int ho, int wo) {
+  const int c4 = c >> 2;
+  size_t total = (size_t)n * ho * wo * c4;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int cg = (int)(i % c4);
+  size_t pix = i / c4;
+  int ow = (int)(pix % wo);
+  size_t t2 = pix / wo;
+  int oh = (int)(t2 % ho);
+  int nb = (int)(t2 / ho);
+  const size_t plane_in = (size_t)n * h * w * c, plane_out = (size_t)n * ho * wo * c;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int a = 0; a < ph; ++a) {
+    int ih = oh * sh - pad_t + a;
+    for (int b = 0; b < pw; ++b) {
+      int iw = ow * sw - pad_l + b;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ih >= 0 && ih < h && iw >= 0 && iw < w)
+        v = act_load4<FMT>(x, plane_in, (((size_t)nb * h + ih) * w + iw) * c + cg * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  act_store4<FMT>(y, plane_out, pix * c + cg * 4, m);
+}
+
+int launch_maxpool(int fmt, const void* x, void* y, int n, int h, int w, int c, int ph, int pw, int sh, int sw,
+                   int pad_t, int pad_l, int ho, int wo, cudaStream_t st) {
+  if (c % 4 != 0) {
+    set_error("maxpool: channels %d not a multiple of 4", c);
+    return DEFER_ERR_INVALID;
+  }
+  size_t total = (size_t)n * ho * wo * (c / 4);
+  unsigned grid = (unsigned)((total + 255) / 256);
+  switch (fmt) {
+    case FMT_F32: maxpool_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16X2: maxpool_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16: maxpool_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    default: set_error("maxpool: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// global average pool: (n, h*w, c) -> (n, c).  One warp-row of channels per block slice; threads
+// stride over channels (coalesced), loop over pixels; pixel range split over threadIdx.y and
+// combined through shared memory.
+// =============================================================================================
+template <int FMT>
+__global__ void __launch_bounds__(256) gap_kernel(const void* __restrict__ x, void* __restrict__ y, int hw, int c) {
+  __shared__ float red[8][32];
+  const int nb = blockIdx.y;
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  const size_t plane_in = (size_t)gridDim.y * hw * c, plane_out = (size_t)gridDim.y * c;
+  float s = 0.f;
+  if (ch < c) {
+    for (int p = threadIdx.y; p < hw; p += 8) s += act_load<FMT>(x, plane_in, ((size_t)nb * hw + p) * c + ch);
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    act_store<FMT>(y, plane_out, (size_t)nb * c + ch, t / (float)hw);
+  }
+}
+
+int launch_gap(int fmt, const void* x, void* y, int n, int h, int w, int c, cudaStream_t st) {
+  dim3 grid((c + 31) / 32, n), block(32, 8);
+  switch (fmt) {
+    case FMT_F32: gap_kernel<FMT_F32><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    case FMT_BF16X2: gap_kernel<FMT_BF16X2><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    case FMT_BF16: gap_kernel<FMT_BF16><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    default: set_error("gap: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// dense: y[b][u] = sum_f x[b][f] * W[f][u] + bias[u].  HBM-bound weight stream at batch 1:
+// thread = output unit (coalesced over u), F split across blockIdx.y for parallelism, partials
+// reduced in a fixed order by a second kernel (deterministic, no atomics).
+// =============================================================================================
+constexpr int DENSE_TB = 128;     // units per block
+constexpr int DENSE_MAXB = 8;     // batch chunk held in registers
+
+int dense_splits(int n, int in_features, int units) {
+  int col_blocks = (units + DENSE_TB - 1) / DENSE_TB;
+  int want = (2 * 148 + col_blocks - 1) / col_blocks;  // ~2 waves of 148 SMs
+  int max_split = (in_features + 31) / 32;              // at least 32 rows per split
+  int s = want < max_split ? want : max_split;
+  int min_split = (in_features + 1023) / 1024;          // keep the x slice of a split small in smem
+  if (s < min_split) s = min_split;
+  return s < 1 ? 1 : s;
+}
+
+template <int FMT, typename WT>
+__global__ void __launch_bounds__(DENSE_TB) dense_partial_kernel(const void* __restrict__ x, const WT* __restrict__ w,
+                                                                 float* __restrict__ partial, int n, int F, int U,
+                                                                 int rows_per_split) {
+  extern __shared__ float xs[];  // [nb_chunk][rows]
+  const int u = blockIdx.x * DENSE_TB + threadIdx.x;
+  const int f0 = blockIdx.y * rows_per_split;
+  const int f1 = min(F, f0 + rows_per_split);
+  const int rows = f1 - f0;
+  const size_t plane = (size_t)n * F;
+  for (int b0 = 0; b0 < n; b0 += DENSE_MAXB) {
+    const int nb = min(DENSE_MAXB, n - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * rows; i += DENSE_TB) {
+      int b = i / rows, f = i - b * rows;
+      xs[b * rows_per_split + f] = act_load<FMT>(x, plane, (size_t)(b0 + b) * F + f0 + f);
+    }
+    __syncthreads();
+    float acc[DENSE_MAXB];
+#pragma unroll
+    for (int b = 0; b < DENSE_MAXB; ++b) acc[b] = 0.f;
+    if (u < U) {
+      const WT* wp = w + (size_t)f0 * U + u;
+#pragma unroll 8
+      for (int f = 0; f < rows; ++f) {
+        float wv;
+        if constexpr (sizeof(WT) == 2) wv = __bfloat162float(wp[(size_t)f * U]);
+        else wv = __ldg(reinterpret_cast<const float*>(wp) + (size_t)f * U);
+#pragma unroll
+        for (int b = 0; b < DENSE_MAXB; ++b)
+          if (b < nb) acc[b] = fmaf(xs[b * rows_per_split + f], wv, acc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < DENSE_MAXB; ++b)
+        if (b < nb) partial[((size_t)blockIdx.y * n + b0 + b) * U + u] = acc[b];
+    }
+  }
+}
+
+template <int FOUT>
+__global__ void __launch_bounds__(256) dense_reduce_kernel(const float* __restrict__ partial,
+                                                           const float* __restrict__ bias, void* __restrict__ y,
+                                                           int n, int U, int splits, uint32_t flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * U;
+  if (i >= total) return;
+  int u = (int)(i % U);
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * total + i];
+  if (bias) s += __ldg(bias + u);
+  if (flags & DEFER_FLAG_RELU) s = fmaxf(s, 0.f);
+  act_store<FOUT>(y, total, i, s);
+}
+
+int launch_dense(int fmt, const void* x, const void* w, bool w_is_bf16, const float* bias, void* y, bool y_is_f32,
+                 float* partial, int n, int F, int U, uint32_t flags, cudaStream_t st) {
+  int splits = dense_splits(n, F, U);
+  int rows = (F + splits - 1) / splits;
+  splits = (F + rows - 1) / rows;
+  dim3 grid((U + DENSE_TB - 1) / DENSE_TB, splits);
+  int nbc = n < DENSE_MAXB ? n : DENSE_MAXB;
+  size_t smem = (size_t)nbc * rows * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("dense: smem %zu too large", smem);
+    return DEFER_ERR_INVALID;
+  }
+#define DENSE_LAUNCH(FM)                                                                                           \
+  if (w_is_bf16)                                                                                                   \
+    dense_partial_kernel<FM, __nv_bfloat16><<<grid, DENSE_TB, smem, st>>>(x, (const __nv_bfloat16*)w, partial, n, F, U, rows); \
+  else                                                                                                             \
+    dense_partial_kernel<FM, float><<<grid, DENSE_TB, smem, st>>>(x, (const float*)w, partial, n, F, U, rows);
+  switch (fmt) {
+    case FMT_F32: DENSE_LAUNCH(FMT_F32); break;
+    case FMT_BF16X2: DENSE_LAUNCH(FMT_BF16X2); break;
+    case FMT_BF16: DENSE_LAUNCH(FMT_BF16); break;
+    default: set_error("dense: bad fmt"); return DEFER_ERR_INVALID;
+  }
+#undef DENSE_LAUNCH
+  DEFER_CUDA(cudaGetLastError());
+  size_t total = (size_t)n * U;
+  unsigned g2 = (unsigned)((total + 255) / 256);
+  int fout = y_is_f32 ? FMT_F32 : fmt;
+  switch (fout) {
+    case FMT_F32: dense_reduce_kernel<FMT_F32><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+    case FMT_BF16X2: dense_reduce_kernel<FMT_BF16X2><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+    case FMT_BF16: dense_reduce_kernel<FMT_BF16><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// softmax over the last axis, one block per row, warp-shuffle max / sum reductions
+// =============================================================================================
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int c) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* xr = x + (size_t)blockIdx.x * c;
+  float* yr = y + (size_t)blockIdx.x * c;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < c; i += 256) m = fmaxf(m, xr[i]);
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < 8 ? red[lane] : -INFINITY;
+    v = warp_max(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  m = bcast;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < c; i += 256) s += expf(xr[i] - m);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < 8 ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  const float inv = 1.f / bcast;
+  for (int i = threadIdx.x; i < c; i += 256) yr[i] = expf(xr[i] - m) * inv;
+}
+
+int launch_softmax(const float* x, float* y, int n, int c, cudaStream_t st) {
+  softmax_kernel<<<n, 256, 0, st>>>(x, y, c);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// standalone elementwise ops (arbitrary cut points): AFFINE (BN), RELU, ADD; 4 channels / thread
+// =============================================================================================
+template <int FMT, int KIND>
+__global__ void __launch_bounds__(256) eltwise_kernel(const void* __restrict__ a, const void* __restrict__ b,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      void* __restrict__ y, size_t n_elems, int c, uint32_t flags) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n_elems) return;
+  float4 v = act_load4<FMT>(a, n_elems, i);
+  if constexpr (KIND == DEFER_OP_AFFINE) {
+    int ch = (int)(i % c);
+    float4 s = scale ? __ldg(reinterpret_cast<const float4*>(scale + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 t = shift ? __ldg(reinterpret_cast<const float4*>(shift + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
+  } else if constexpr (KIND == DEFER_OP_ADD) {
+    float4 u = act_load4<FMT>(b, n_elems, i);
+    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  }
+  if (KIND == DEFER_OP_RELU || (flags & DEFER_FLAG_RELU)) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  act_store4<FMT>(y, n_elems, i, v);
+}
+
+template <int FMT>
+static int launch_eltwise_t(int kind, const void* a, const void* b, const float* scale, const float* shift, void* y,
+                            size_t n_elems, int c, uint32_t flags, cudaStream_t st) {
+  unsigned grid = (unsigned)((n_elems / 4 + 255) / 256);
+  switch (kind) {
+    case DEFER_OP_AFFINE: eltwise_kernel<FMT, DEFER_OP_AFFINE><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    case DEFER_OP_RELU: eltwise_kernel<FMT, DEFER_OP_RELU><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    case DEFER_OP_ADD: eltwise_kernel<FMT, DEFER_OP_ADD><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    default: set_error("eltwise: bad kind %d", kind); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+int launch_eltwise(int fmt, int kind, const void* a, const void* b, const float* scale, const float* shift, void* y,
+                   size_t n_pix, int c, uint32_t flags, cudaStream_t st) {
+  if (c % 4 != 0) {
+    set_error("eltwise: channels %d not a multiple of 4", c);
+    return DEFER_ERR_INVALID;
+  }
+  size_t n_elems = n_pix * (size_t)c;
+  switch (fmt) {
+    case FMT_F32: return launch_eltwise_t<FMT_F32>(kind, a, b, scale, shift, y, n_elems, c, flags, st);
+    case FMT_BF16X2: return launch_eltwise_t<FMT_BF16X2>(kind, a, b, scale, shift, y, n_elems, c, flags, st);
+    case FMT_BF16: return launch_eltwise_t<FMT_BF16>(kind, a, b, scale, shift, y, n_elems, c, flags, st);
+  }
+  set_error("eltwise: bad fmt");
+  return DEFER_ERR_INVALID;
+}
+
+// standalone ZeroPadding2D (scalar; only reached for exotic cut points)
+template <int FMT>
+__global__ void __launch_bounds__(256) pad_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w,
+                                                  int c, int pad_t, int pad_l, int ho, int wo) {
+  size_t total = (size_t)n * ho * wo * c;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ch = (int)(i % c);
+  size_t pix = i / c;
+  int ow = (int)(pix % wo);
+  size_t t2 = pix / wo;
+  int oh = (int)(t2 % ho);
+  int nb = (int)(t2 / ho);
+  int ih = oh - pad_t, iw = ow - pad_l;
+  float v = 0.f;
+  if (ih >= 0 && ih < h && iw >= 0 && iw < w)
+    v = act_load<FMT>(x, (size_t)n * h * w * c, (((size_t)nb * h + ih) * w + iw) * c + ch);
+  act_store<FMT>(y, total, i, v);
+}
+
+int launch_pad(int fmt, const void* x, void* y, int n, int h, int w, int c, int pad_t, int pad_l, int ho, int wo,
+               cudaStream_t st) {
+  size_t total = (size_t)n * ho * wo * c;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  switch (fmt) {
+    case FMT_F32: pad_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16X2: pad_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16: pad_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    default: set_error("pad: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// format conversion
+// =============================================================================================
+template <int FMT>
+__global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ x, void* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) act_store<FMT>(y, n, i, x[i]);
+}
+template <int FMT>
+__global__ void __launch_bounds__(256) decode_kernel(const void* __restrict__ x, float* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = act_load<FMT>(x, n, i);
+}
+template <int FMT>
+__global__ void __launch_bounds__(256) copy_act_kernel(const void* __restrict__ x, void* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) act_store<FMT>(y, n, i, act_load<FMT>(x, n, i));
+}
+
+int launch_encode(int fmt, const float* x, void* y, size_t n, cudaStream_t st) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  switch (fmt) {
+    case FMT_F32: encode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16X2: encode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16: encode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
+    default: set_error("encode: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+int launch_decode(int fmt, const void* x, float* y, size_t n, cudaStream_t st) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  switch (fmt) {
+    case FMT_F32: decode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16X2: decode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16: decode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
+    default: set_error("decode: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+int launch_copy_act(int fmt, const void* x, void* y, size_t n, cudaStream_t st) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  switch (fmt) {
+    case FMT_F32: copy_act_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16X2: copy_act_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16: copy_act_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
+    default: set_error("copy: bad fmt"); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(x[i]);
+}
+int launch_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t st) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  f32_to_bf16_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
+// hop flags.  Each slot is used strictly in sequence, so the k-th use waits for / publishes the
+// value k; the running count lives in device memory so the kernels are CUDA-graph friendly.
+//   wait:   want = ++(*counter) - minus;  spin until *flag >= want   (acquire, system scope)
+//   signal: v = ++(*counter);  fence.sys;  *remote_flag = v          (release, system scope)
+// A wait that exceeds its budget records DEFER_ERR_TIMEOUT in *status and returns (never hangs).
+// =============================================================================================
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t* counter, int minus, int* status,
+                                 unsigned long long timeout_ns) {
+  if (threadIdx.x != 0) return;
+  uint32_t want = ++(*counter) - (uint32_t)minus;
+  if (want == 0) return;
+  if (*reinterpret_cast<volatile int*>(status) != 0) return;  // pipeline already failed: do not spin again
+  unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < want) {
+    if ((++spins & 0x3ff) == 0) {
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        atomicExch(status, (int)DEFER_ERR_TIMEOUT);
+        break;
+      }
+    }
+    __nanosleep(64);
+  }
+}
+
+__global__ void signal_flag_kernel(uint32_t* remote_flag, uint32_t* counter) {
+  if (threadIdx.x != 0) return;
+  uint32_t v = ++(*counter);
+  __threadfence_system();
+  st_release_sys(remote_flag, v);
+}
+
+int launch_wait_flag(const uint32_t* flag, uint32_t* counter, int minus, int* status, unsigned long long timeout_ns,
+                     cudaStream_t st) {
+  wait_flag_kernel<<<1, 32, 0, st>>>(flag, counter, minus, status, timeout_ns);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, cudaStream_t st) {
+  signal_flag_kernel<<<1, 32, 0, st>>>(remote_flag, counter);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+}  // namespace defer

@@ -1,0 +1,206 @@
+"""Dispatcher with the reference's API (``/root/reference/src/dispatcher.py:20-115``).
+
+``DEFER(computeNodes).run_defer(model, partition_layers, input_stream, output_stream)`` - same names,
+same arguments, same blocking behaviour (callers run it in a daemon thread, ``test/test.py:42``).
+What changed underneath:
+
+* ``computeNodes[i]`` is a GPU ordinal (or ``"cuda:i"``) of one 8xB200 box instead of an IP;
+* ``_dispatchModels`` still ships ``to_json()`` + ``get_weights()`` per stage (``dispatcher.py:49,57``)
+  but "shipping" is an upload into that GPU's HBM through ``defer_stage_create`` (same process) or a
+  ``torch.distributed`` object send to the rank that owns the GPU (one process per GPU);
+* ``_startDistEdgeInference`` / ``_result_server`` (``dispatcher.py:85-105``) keep their roles - feed
+  the first stage from ``input_stream``, drain the last into ``output_stream`` in FIFO order - over
+  pinned-memory DMA instead of ZFP+LZ4+TCP.
+
+Non-reference additions: ``close()`` / context manager (the reference can only be killed), keyword-only
+``dtype``, ``depth`` (in-flight microbatches) and ``batch``.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from . import keras_like as K
+from .dag_util import construct_model
+from .node import DTYPE_TO_FMT, StageRunner, parse_device
+
+
+class DEFER:
+    def __init__(self, computeNodes, *, dtype: str = "float32", depth: int = 4, batch: Optional[int] = None,
+                 conv_backend: int = 0, dist=None, wait_timeout_ms: int = 0) -> None:
+        self.computeNodes = list(computeNodes)
+        self.dispatchIP = "localhost"       # reference: socket.gethostbyname(...) (dispatcher.py:23); no sockets here
+        self.chunk_size = 512 * 1000        # kept for interface parity (dispatcher.py:24)
+        self.dtype = dtype
+        self.depth = int(depth)
+        self.batch = batch
+        self.conv_backend = conv_backend
+        self.dist = dist                    # DistContext when launched one-process-per-GPU
+        self.wait_timeout_ms = wait_timeout_ms
+        self.stages: List[StageRunner] = []
+        self._stop = threading.Event()
+        self._ready = threading.Event()
+        self._inflight: Optional[threading.Semaphore] = None
+        self._submitted = 0
+        self._threads: List[threading.Thread] = []
+        self._error: Optional[BaseException] = None
+        self.results_delivered = 0
+
+    # ------------------------------------------------------------------ partition (dispatcher.py:27-42)
+    def _partition(self, model: K.Model, layer_parts: List[str]) -> List[K.Model]:
+        models = []
+        for p in range(len(layer_parts) + 1):
+            if p == 0:
+                start = model.input._keras_history[0].name
+            else:
+                start = layer_parts[p - 1]
+            if p == len(layer_parts):
+                end = model.output._keras_history[0].name
+            else:
+                end = layer_parts[p]
+            part = construct_model(model, start, end, part_name=f"part{p+1}")
+            models.append(part)
+        return models
+
+    # ------------------------------------------------------------------ placement (dispatcher.py:44-65)
+    def _dispatchModels(self, models: list, nodeIPs: List) -> None:
+        if len(nodeIPs) < len(models):
+            raise ValueError(f"{len(models)} stages but only {len(nodeIPs)} compute nodes")
+        n = len(models)
+        batch = self.batch or 1
+        if self.dist is not None:
+            # one process per GPU: ship (json, weights, next hop) to each rank; ranks build + link themselves
+            for i in range(n):
+                next_node = nodeIPs[i + 1] if i != n - 1 else self.dispatchIP
+                self.dist.send_stage(i, {"json": models[i].to_json(), "weights": models[i].get_weights(),
+                                         "next_node": str(next_node), "fmt": self.dtype, "batch": batch,
+                                         "depth": self.depth, "conv_backend": self.conv_backend,
+                                         "wait_timeout_ms": self.wait_timeout_ms})
+            self.dist.wait_all_ready()      # the 1-byte ACK of dispatcher.py:64-65
+            return
+        runners = []
+        for i in range(n):
+            model_json = models[i].to_json()
+            weights = models[i].get_weights()
+            r = StageRunner.from_wire(model_json, weights, device=parse_device(nodeIPs[i]), dtype=self.dtype,
+                                      max_batch=batch, depth=self.depth, is_first=(i == 0), is_last=(i == n - 1),
+                                      finalize=False, conv_backend=self.conv_backend,
+                                      wait_timeout_ms=self.wait_timeout_ms)
+            r.name = f"part{i+1}"
+            runners.append(r)
+        for i in range(n - 1):              # next hop = nodeIPs[i+1] (dispatcher.py:51-55)
+            runners[i].link_to(runners[i + 1])
+        for r in runners:
+            r.finalize()
+        self.stages = runners
+
+    # ------------------------------------------------------------------ ingress (dispatcher.py:85-93)
+    def _startDistEdgeInference(self, input: queue.Queue):
+        first = self.stages[0] if self.stages else self.dist.local_runner()
+        try:
+            while not self._stop.is_set():
+                try:
+                    model_input = input.get(timeout=0.05)
+                except queue.Empty:
+                    continue
+                while not self._inflight.acquire(timeout=0.05):
+                    if self._stop.is_set():
+                        return
+                seq = self._submitted
+                x = np.asarray(model_input)
+                if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+                    x = np.ascontiguousarray(x, dtype=np.float32)
+                self._hold[seq % len(self._hold)] = x   # keep alive until the DMA has certainly happened
+                first.submit(seq, x)
+                if self.dist is not None:
+                    first.step(seq)
+                    self.dist.mark_submitted(seq + 1)
+                else:
+                    for r in self.stages:
+                        r.step(seq)
+                self._submitted = seq + 1
+        except BaseException as e:  # surface in close()/run_defer instead of dying silently
+            self._error = e
+            self._stop.set()
+
+    # ------------------------------------------------------------------ egress (dispatcher.py:95-105)
+    def _result_server(self, output: queue.Queue):
+        try:
+            self._ready.wait()
+            seq = 0
+            local_last = bool(self.stages) or (self.dist is not None and self.dist.world == 1)
+            last = (self.stages[-1] if self.stages else self.dist.local_runner()) if local_last else None
+            while not self._stop.is_set():
+                if seq >= self._submitted:
+                    time.sleep(20e-6)
+                    continue
+                if last is not None:
+                    pred = last.result(seq)
+                else:
+                    pred = self.dist.wait_result(seq, self._stop)
+                    if pred is None:
+                        return
+                self._inflight.release()
+                seq += 1
+                self.results_delivered = seq
+                while not self._stop.is_set():
+                    try:
+                        output.put(pred, timeout=0.05)
+                        break
+                    except queue.Full:
+                        continue
+        except BaseException as e:
+            self._error = e
+            self._stop.set()
+
+    # ------------------------------------------------------------------ orchestration (dispatcher.py:107-115)
+    def run_defer(self, model: K.Model, partition_layers, input_stream: queue.Queue, output_stream: queue.Queue):
+        if self.batch is None:
+            self.batch = 1
+        models_to_dispatch = self._partition(model, partition_layers)
+        self._inflight = threading.Semaphore(self.depth)
+        self._hold = [None] * (2 * self.depth + 2)
+        a = threading.Thread(target=self._result_server, args=(output_stream,), name="defer-result")
+        a.start()
+        try:
+            self._dispatchModels(models_to_dispatch, self.computeNodes)
+        except BaseException as e:
+            self._error = e
+            self._stop.set()
+            self._ready.set()
+            a.join()
+            raise
+        self._ready.set()
+        b = threading.Thread(target=self._startDistEdgeInference, args=(input_stream,), daemon=True, name="defer-feed")
+        b.start()
+        self._threads = [a, b]
+        a.join()                            # blocks until close(), like the reference blocks forever
+        b.join()
+        if self._error is not None:
+            raise self._error
+
+    # ------------------------------------------------------------------ non-reference: clean shutdown
+    def wait_ready(self, timeout: Optional[float] = None) -> bool:
+        return self._ready.wait(timeout)
+
+    def close(self):
+        self._stop.set()
+        for t in self._threads:
+            if t is not threading.current_thread():
+                t.join(timeout=10)
+        if self.dist is not None:
+            self.dist.request_stop()
+        for r in self.stages:
+            r.close()
+        self.stages = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

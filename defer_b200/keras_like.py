@@ -199,8 +199,11 @@ class InputLayer(Layer):
         self.built = True
         node = Node(self, [])
         if input_tensor is not None:
-            # TF 1.x InputLayer(input_tensor=t) re-tags t itself: t._keras_history = (self, 0, 0).
-            input_tensor._keras_history = (self, 0, 0)
+            # TF 1.x InputLayer(input_tensor=t) returns t itself and re-tags t._keras_history; here the
+            # SAME tensor object is kept (so Model(inputs=start.output, ...) of src/dag_util.py:30 sees it)
+            # and the new input layer is recorded as an alias instead of overwriting the history - the
+            # original model stays intact and can be partitioned again.
+            input_tensor._input_alias = (self, 0, 0)
             node.output_tensor = input_tensor
         else:
             node.output_tensor = SymbolicTensor(self.batch_input_shape, self, 0, f"{self.name}:0")
@@ -212,9 +215,9 @@ class InputLayer(Layer):
 
 def Input(shape: Optional[Sequence[int]] = None, tensor: Optional[SymbolicTensor] = None,
           name: Optional[str] = None) -> SymbolicTensor:
-    """``tf.keras.Input``.  With ``tensor=`` the SAME tensor object is returned, re-tagged as the
-    output of a new ``InputLayer`` - what TF 1.x does and what reference ``src/dag_util.py:28,30``
-    relies on (``Model(inputs=model.get_layer(start).output, ...)`` passes the original tensor)."""
+    """``tf.keras.Input``.  With ``tensor=`` the SAME tensor object is returned, standing for the output
+    of a new ``InputLayer`` named ``name`` - what reference ``src/dag_util.py:28,30`` relies on
+    (``Model(inputs=model.get_layer(start).output, ...)`` passes the original tensor)."""
     if tensor is not None:
         layer = InputLayer(tensor.shape, name=name, input_tensor=tensor)
         return layer.output
@@ -447,12 +450,18 @@ class Model:
         in_progress = set()
         node_inputs: Dict[Tuple[int, int], List[SymbolicTensor]] = {}
 
+        def hist(t: SymbolicTensor):
+            # a model input given as Input(tensor=t) is produced by its alias InputLayer in THIS model
+            if id(t) in input_ids and getattr(t, "_input_alias", None) is not None:
+                return t._input_alias
+            return t._keras_history
+
         def build_map(tensor: SymbolicTensor) -> None:
             # iterative DFS: recursion depth would exceed Python's limit on ResNet152
             stack = [(tensor, 0)]
             while stack:
                 t, state = stack.pop()
-                layer, node_index, _ = t._keras_history
+                layer, node_index, _ = hist(t)
                 key = (id(layer), node_index)
                 if state == 0:
                     if key in finished:
@@ -492,20 +501,22 @@ class Model:
             node_depth[key] = d
             layer_depth[layer] = d
             for it in node_inputs[key]:
-                il, ini, _ = it._keras_history
+                il, ini, _ = hist(it)
                 ikey = (id(il), ini)
                 node_depth[ikey] = max(d + 1, node_depth.get(ikey, 0))
         # the model's input tensors are represented by (possibly synthetic) input layers at max depth
-        self._input_keys = {(id(t._keras_history[0]), t._keras_history[1]) for t in self.inputs}
+        self._input_keys = {(id(hist(t)[0]), hist(t)[1]) for t in self.inputs}
+        # frozen now: a later Input(tensor=...) on the same tensor (another partition) changes its alias
+        self._input_layers = [hist(t)[0] for t in self.inputs]
+        self._output_layers = [t._keras_history[0] for t in self.outputs]
         max_d = max(layer_depth.values()) if layer_depth else 0
-        for t in self.inputs:
-            layer_depth[t._keras_history[0]] = max_d
+        for l in self._input_layers:
+            layer_depth[l] = max_d
 
         layers = sorted(layer_depth.keys(), key=lambda l: (-layer_depth[l], layer_indices[l]))
         self._node_order = order
         self._node_inputs = node_inputs
-        # names frozen now: a later Input(tensor=...) on this graph re-tags tensor histories
-        self._node_input_names = {k: [t._keras_history[0].name for t in v] for k, v in node_inputs.items()}
+        self._node_input_names = {k: [hist(t)[0].name for t in v] for k, v in node_inputs.items()}
         self._layer_depth = layer_depth
         # Layers whose *output* is the model input stand in as the InputLayer of this model.
         self.layers: List[Layer] = layers
@@ -532,7 +543,7 @@ class Model:
 
     # -- weights
     def _weighted_layers(self) -> List[Layer]:
-        inputs = {t._keras_history[0] for t in self.inputs}
+        inputs = set(self._input_layers)
         return [l for l in self.layers if l not in inputs and l.weight_shapes()]
 
     def get_weights(self) -> List[np.ndarray]:
@@ -555,7 +566,7 @@ class Model:
 
     # -- serialisation (stage wire format, reference src/dispatcher.py:49 / src/node.py:31)
     def get_config(self) -> dict:
-        input_layers = {t._keras_history[0] for t in self.inputs}
+        input_layers = set(self._input_layers)
         layer_cfgs = []
         inbound: Dict[str, List[str]] = {}
         for layer, ins in self.iter_nodes():
@@ -564,7 +575,7 @@ class Model:
             if l in input_layers:
                 shape = l.output.shape if l._inbound_nodes else None
                 # the input tensor of a sub-model is the output of the cut layer: serialise as InputLayer
-                t = next(t for t in self.inputs if t._keras_history[0] is l)
+                t = self.inputs[self._input_layers.index(l)]
                 layer_cfgs.append({"name": l.name, "class_name": "InputLayer",
                                    "config": {"name": l.name, "batch_input_shape": list(t.shape),
                                               "dtype": "float32"},
@@ -573,8 +584,8 @@ class Model:
                 layer_cfgs.append({"name": l.name, "class_name": l.class_name, "config": l.get_config(),
                                    "inbound_nodes": [[[n, 0, 0, {}] for n in inbound[l.name]]]})
         return {"name": self.name, "layers": layer_cfgs,
-                "input_layers": [[t._keras_history[0].name, 0, 0] for t in self.inputs],
-                "output_layers": [[t._keras_history[0].name, 0, 0] for t in self.outputs]}
+                "input_layers": [[l.name, 0, 0] for l in self._input_layers],
+                "output_layers": [[l.name, 0, 0] for l in self._output_layers]}
 
     def to_json(self) -> str:
         return json.dumps({"class_name": "Model", "config": self.get_config(),
