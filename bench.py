@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py - ResNet50 pipeline-partitioned inference throughput on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one microbatch (reference: one 224x224x3 image, test/test.py:22,47-49) through the whole
+N-stage pipeline.  Stage i lives on GPU i (one process per GPU under torchrun); the cut list is the
+reference's for 8 stages (test/test.py:18) and SURVEY.md 8d's for 2 / 4.
+
+value  : inferences/s with the input image already resident in the first stage's HBM slot (the reference
+         test enqueues the same image 1000x), device-timed with CUDA events, max over ranks.
+e2e    : the same K inferences through the public API (DEFER.run_defer + queue.Queue), host buffers pinned,
+         one H2D of the image and one D2H of the probabilities per step inside the timed region.
+roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+--impl reference : the CPU port of the reference path (oracle/torch_cpu.py, all host cores) on the same
+         workload - TensorFlow itself is not installable here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import queue
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "resnet152", "vgg16"])
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float32_simt", "bfloat16"])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--depth", type=int, default=0, help="in-flight microbatches (lanes); 0 = auto")
+    ap.add_argument("--conv-backend", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    return ap.parse_args()
+
+
+def build_model(name):
+    from defer_b200 import applications
+    return {"resnet50": applications.ResNet50, "resnet152": applications.ResNet152, "vgg16": applications.VGG16}[name]()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU port
+def cpu_reference_run(model, n_stages, x, steps, warmup, seconds=None):
+    """Times the oracle port of the reference path on the host cores.
+    1 stage : test/local_infer.py:16-23 (predict in a loop).  N stages: test/test.py with threads standing in
+    for nodes and an in-memory identity hop (the reference hop is a lossless codec)."""
+    import torch
+    from defer_b200 import applications, dag_util
+    from oracle.torch_cpu import TorchCpuModel
+    cuts = applications.default_cuts(model, n_stages)
+    names = [model.input._keras_history[0].name] + cuts + [model.output._keras_history[0].name]
+    parts = [dag_util.construct_model(model, names[i], names[i + 1], part_name=f"part{i+1}") for i in range(n_stages)]
+    stages = [TorchCpuModel(p.to_json(), p.get_weights()) for p in parts]
+    cores = torch.get_num_threads()
+    if n_stages == 1:
+        for _ in range(warmup):
+            stages[0].predict(x)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            stages[0].predict(x)
+            n += 1
+            if (seconds is not None and time.perf_counter() - t0 >= seconds) or (seconds is None and n >= steps):
+                break
+        dt = time.perf_counter() - t0
+        return n / dt, dt / n * 1e3, cores, n
+    torch.set_num_threads(max(1, cores // n_stages))   # N stage threads share the host cores
+    qs = [queue.Queue(8) for _ in range(n_stages + 1)]
+
+    def worker(i):
+        while True:
+            item = qs[i].get()
+            if item is None:
+                qs[i + 1].put(None)
+                return
+            qs[i + 1].put(stages[i].predict(item))
+
+    ths = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n_stages)]
+    for t in ths:
+        t.start()
+    total = warmup + steps
+    def feeder():
+        for _ in range(total):
+            qs[0].put(x)
+        qs[0].put(None)
+    threading.Thread(target=feeder, daemon=True).start()
+    for _ in range(warmup):
+        qs[-1].get()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        qs[-1].get()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, cores, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    model = build_model(args.model)
+    from defer_b200 import applications
+    x = applications.synthetic_input(args.batch)
+    steps = min(args.steps, 400)
+    val, ms, cores, n = cpu_reference_run(model, args.gpus, x, steps, max(3, min(args.warmup, 10)))
+    val *= args.batch
+    sample = f"{n} predict calls of {args.model} batch {args.batch}, {args.gpus} stage(s), torch CPU (oneDNN) port"
+    line = {"impl": "reference", "metric": "inferences_per_sec", "value": val, "unit": "inferences/s",
+            "n_gpus": args.gpus, "steps": n, "warmup": max(3, min(args.warmup, 10)), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, depth=None),
+            "cpu_baseline": {"value": val, "unit": "inferences/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "TensorFlow 1.x reference not installable (SURVEY.md 8c); oracle/torch_cpu.py port"},
+            "e2e": {"value": val, "unit": "inferences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cpus": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, depth):
+    return {"workload": f"{args.model} {args.gpus}-stage pipeline, batch {args.batch}, 224x224x3 synthetic image, "
+                        f"{'fp32 parity path (bf16x3 on tcgen05)' if args.dtype == 'float32' else args.dtype}",
+            "model": args.model, "stages": args.gpus, "batch": args.batch, "depth": depth,
+            "parallelism": f"pp{args.gpus}",
+            "l2": "not flushed between steps: steady-state pipeline re-reads the same weights every microbatch by "
+                  "design; the per-kernel roofline numbers are taken with a 256 MB L2 flush between launches"}
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    from defer_b200 import _cabi
+    _cabi.load()                      # before torch initialises CUDA (sets CUDA_DEVICE_MAX_CONNECTIONS)
+    import torch
+    from defer_b200 import applications, dag_util
+    from defer_b200.dispatcher import DEFER
+    from defer_b200.node import Node, StageRunner, pinned_empty
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus}")
+        args.gpus = world
+    n_stages = args.gpus
+    depth = args.depth or (8 if n_stages == 1 else 6)
+    K, W, B = args.steps, max(args.warmup, 3), args.batch
+
+    ctx = None
+    if world > 1:
+        from defer_b200.dist import DistContext
+        ctx = DistContext(ring=max(64, 2 * depth), out_elems=1000, batch=B)
+    torch.cuda.set_device(local_rank)
+
+    model = build_model(args.model) if rank == 0 else None
+    x_host = pinned_empty((B, 224, 224, 3))
+    x_host[...] = applications.synthetic_input(B)
+
+    # ---- build the pipeline through the public pieces (DEFER partition + dispatch)
+    defer = DEFER(list(range(n_stages)), dtype=args.dtype, depth=depth, batch=B, conv_backend=args.conv_backend, dist=ctx)
+    in_q, out_q = queue.Queue(depth), queue.Queue(4 * depth)
+    node_thread = None
+    if ctx is not None:
+        node = Node(dist_ctx=ctx, device=local_rank)
+        node_thread = threading.Thread(target=node.run, name="defer-node", daemon=True)
+        node_thread.start()
+    t_defer = None
+    if rank == 0:
+        cuts = applications.default_cuts(model, n_stages)
+        t_defer = threading.Thread(target=defer.run_defer, args=(model, cuts, in_q, out_q), daemon=True)
+        t_defer.start()
+        if not defer.wait_ready(600):
+            raise SystemExit("pipeline did not come up")
+        if defer._error:
+            raise defer._error
+    if ctx is not None:
+        runner = ctx.local_runner()
+    else:
+        runner = defer.stages[0]
+    my_stages = defer.stages if ctx is None else [runner]
+
+    def barrier_sync():
+        if ctx is not None:
+            ctx.barrier()
+        torch.cuda.synchronize()
+        for r in my_stages:
+            r.sync()
+
+    result = {}
+    # =========================================================================== e2e through DEFER + queues
+    if not args.no_e2e:
+        def e2e_pass(n):
+            if rank == 0:
+                def feed():
+                    for _ in range(n):
+                        in_q.put(x_host)
+                th = threading.Thread(target=feed, daemon=True)
+                th.start()
+                last = None
+                for _ in range(n):
+                    last = out_q.get(timeout=300)
+                th.join()
+                return last
+            return None
+        e2e_pass(W)
+        barrier_sync()
+        t0 = time.perf_counter()
+        last = e2e_pass(K)
+        barrier_sync()
+        dt = time.perf_counter() - t0
+        dt = ctx.max_over_ranks(dt) if ctx is not None else dt
+        result["e2e"] = {"value": K * B / dt, "unit": "inferences/s", "h2d_bytes_per_step": int(x_host.nbytes),
+                         "d2h_bytes_per_step": int(B * 1000 * 4), "ms_per_step": dt / K * 1e3,
+                         "timing": "host wall clock between barrier+synchronize points (the API is host queues)",
+                         "api": "DEFER.run_defer(model, cuts, queue.Queue, queue.Queue)"}
+        if rank == 0:
+            result["probs_sum"] = float(np.asarray(last).sum())
+
+    # =========================================================================== device-timed steady state
+    # Drive the stages directly (same lanes / graphs), input resident in the first stage's slots.
+    seq0 = defer._submitted if rank == 0 else 0
+    if ctx is not None:
+        seq0 = int(ctx.max_over_ranks(seq0))
+    if rank == 0:
+        # make every input slot of stage 0 hold the image (resident): one submit per lane
+        first = my_stages[0]
+        for d in range(depth):
+            first.submit(seq0 + d, x_host)   # lands in slot (seq0+d) % depth, stays there
+        first.sync()
+
+    def direct_pass(n, start):
+        """Issue n microbatches with at most `depth` in flight.  Returns the next sequence number."""
+        if ctx is None:
+            last = my_stages[-1]
+            inflight = 0
+            out = np.empty(last.out_shape, np.float32)
+            for s in range(start, start + n):
+                if inflight == depth:
+                    last.result(s - depth, out)
+                    inflight -= 1
+                for r in my_stages:
+                    r.step(s)
+                inflight += 1
+            for s in range(start + n - inflight, start + n):
+                last.result(s, out)
+            return start + n
+        # one process per GPU: rank 0 steps stage 0 and publishes `submitted`; node loops follow
+        if rank == 0:
+            for s in range(start, start + n):
+                while s - ctx.done() >= depth:
+                    pass
+                runner.step(s)
+                ctx.mark_submitted(s + 1)
+            while ctx.done() < start + n:
+                time.sleep(20e-6)
+        else:
+            while ctx.done() < start + n and not ctx.stop_requested():
+                time.sleep(50e-6)
+        return start + n
+
+    sampler = ClockSampler(local_rank)
+    seq = direct_pass(W, seq0)
+    barrier_sync()
+    if rank == 0:
+        sampler.start()
+    for r in my_stages:
+        r.timer_start()
+    t0 = time.perf_counter()
+    seq = direct_pass(K, seq)
+    ms = max(r.timer_stop() for r in my_stages)
+    wall = time.perf_counter() - t0
+    barrier_sync()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ctx.max_over_ranks(ms) if ctx is not None else ms
+    wall = ctx.max_over_ranks(wall) if ctx is not None else wall
+    launches = sum(r.num_kernels() for r in my_stages) * K
+    launches = int(ctx.sum_over_ranks(launches)) if ctx is not None else launches
+
+    # =========================================================================== roofline + CPU baseline (N=1 only)
+    peaks = load_peaks()
+    roofline = None
+    stage_table = None
+    if rank == 0 and not args.no_roofline and ctx is None:
+        r0 = my_stages[0]
+        rows = []
+        for i in range(len(r0.plan.ops)):
+            info = r0.op_info(i)
+            us = r0.time_op(i, iters=10, flush_l2=True)
+            us_hot = r0.time_op(i, iters=20, flush_l2=False)
+            info.update({"op": i, "us_cold": us, "us_hot": us_hot})
+            rows.append(info)
+        conv = [r for r in rows if r["kernel"].startswith("conv_umma")] or [r for r in rows if r["kernel"].startswith("conv")]
+        by = sum(r["alg_bytes"] for r in conv)
+        fl = sum(r["alg_flops"] for r in conv)
+        t_cold = sum(r["us_cold"] for r in conv) * 1e-6
+        t_hot = sum(r["us_hot"] for r in conv) * 1e-6
+        t_all = sum(r["us_hot"] for r in rows) * 1e-6
+        top = max(conv, key=lambda r: r["us_cold"])
+        bound_hbm_t = by / (peaks["hbm_gbs"] * 1e9)
+        bound_tc_t = fl / (peaks["bf16_tflops"] * 1e12)
+        roofline = {"kernel": conv[0]["kernel"], "launches_per_step": len(conv),
+                    "bound": "hbm" if bound_hbm_t >= bound_tc_t else "tensor",
+                    "achieved": by / t_cold / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": by / t_cold / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source"] + " (burst copy bandwidth, kernel timed alone)",
+                    "alg_bytes_per_step": by, "alg_flops_per_step": fl,
+                    "achieved_tflops": fl / t_cold / 1e12,
+                    "hot_l2": {"achieved": by / t_hot / 1e9, "frac": by / t_hot / 1e9 / peaks["hbm_gbs"],
+                               "note": "same launches back-to-back without L2 flush (weights L2-resident)"},
+                    "share_of_step": t_hot / t_all if t_all else None,
+                    "top_launch": {"layers": top["layers"], "us_cold": top["us_cold"], "us_hot": top["us_hot"],
+                                   "alg_bytes": top["alg_bytes"], "gbs_cold": top["alg_bytes"] / top["us_cold"] / 1e3},
+                    "method": "CUDA events on the launching stream, 10 launches per op, 256 MB L2 flush between launches"}
+        stage_table = [{"op": r["op"], "kernel": r["kernel"], "layers": r["layers"][:2], "us_cold": round(r["us_cold"], 2),
+                        "us_hot": round(r["us_hot"], 2), "alg_MB": round(r["alg_bytes"] / 1e6, 3),
+                        "alg_GF": round(r["alg_flops"] / 1e9, 4)} for r in rows]
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu and n_stages == 1:
+        val, msc, cores, n = cpu_reference_run(model, 1, np.array(x_host), 0, 3, seconds=args.cpu_seconds)
+        cpu_baseline = {"value": val * B, "unit": "inferences/s", "cores": cores, "kind": "port",
+                        "sample": f"{n} predict calls in {args.cpu_seconds:.0f} s of {args.model} batch {B} "
+                                  "(oracle/torch_cpu.py, oneDNN, all host threads; test/local_infer.py protocol)",
+                        "host_cpus": os.cpu_count()}
+
+    # =========================================================================== shut down + report
+    if rank == 0:
+        defer.close()
+    if ctx is not None:
+        ctx.shutdown(node_thread)
+    if rank == 0:
+        line = {"metric": "inferences_per_sec", "value": K * B / (ms * 1e-3), "unit": "inferences/s", "n_gpus": n_stages,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": {"float32": "bf16x3->f32", "float32_simt": "f32", "bfloat16": "bf16"}[args.dtype],
+                "data": "synthetic", "config": workload_config(args, depth), "clocks": clocks,
+                "gpu_launches": launches, "wall_ms_per_step": wall / K * 1e3,
+                "timing": "CUDA events per rank (first launch -> all lanes drained), max over ranks"}
+        line.update(result)
+        if roofline is not None:
+            line["roofline"] = roofline
+            line["ops"] = stage_table
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

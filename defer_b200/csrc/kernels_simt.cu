@@ -476,6 +476,22 @@ __global__ void __launch_bounds__(256) eltwise_kernel(const void* __restrict__ a
   act_store4<FMT>(y, n_elems, i, v);
 }
 
+// ReLU on the BF16X2 format works on the planes directly: an element either passes through with its
+// (hi, lo) pair untouched or becomes (0, 0).  Re-splitting hi+lo could pick the other representation of
+// the same value at rounding ties, which would make results depend on where the model is cut.
+__global__ void __launch_bounds__(256) relu_planes_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ y,
+                                                          size_t n_pairs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one bf16 pair of the hi plane (and of the lo plane)
+  if (i >= n_pairs) return;
+  uint32_t h = x[i], l = x[n_pairs + i];
+  // keep an element iff hi > 0 (sign bit clear and non-zero); |lo| <= ulp(hi)/2 never flips the sign
+  uint32_t keep_lo = ((h & 0x8000u) == 0 && (h & 0x7fffu) != 0) ? 0x0000ffffu : 0u;
+  uint32_t keep_hi = ((h & 0x80000000u) == 0 && (h & 0x7fff0000u) != 0) ? 0xffff0000u : 0u;
+  uint32_t m = keep_lo | keep_hi;
+  y[i] = h & m;
+  y[n_pairs + i] = l & m;
+}
+
 template <int FMT>
 static int launch_eltwise_t(int kind, const void* a, const void* b, const float* scale, const float* shift, void* y,
                             size_t n_elems, int c, uint32_t flags, cudaStream_t st) {
@@ -497,6 +513,12 @@ int launch_eltwise(int fmt, int kind, const void* a, const void* b, const float*
     return DEFER_ERR_INVALID;
   }
   size_t n_elems = n_pix * (size_t)c;
+  if (fmt == FMT_BF16X2 && kind == DEFER_OP_RELU) {
+    size_t n_pairs = n_elems / 2;
+    relu_planes_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>((const uint32_t*)a, (uint32_t*)y, n_pairs);
+    DEFER_CUDA(cudaGetLastError());
+    return DEFER_OK;
+  }
   switch (fmt) {
     case FMT_F32: return launch_eltwise_t<FMT_F32>(kind, a, b, scale, shift, y, n_elems, c, flags, st);
     case FMT_BF16X2: return launch_eltwise_t<FMT_BF16X2>(kind, a, b, scale, shift, y, n_elems, c, flags, st);
@@ -553,12 +575,6 @@ __global__ void __launch_bounds__(256) decode_kernel(const void* __restrict__ x,
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = act_load<FMT>(x, n, i);
 }
-template <int FMT>
-__global__ void __launch_bounds__(256) copy_act_kernel(const void* __restrict__ x, void* __restrict__ y, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) act_store<FMT>(y, n, i, act_load<FMT>(x, n, i));
-}
-
 int launch_encode(int fmt, const float* x, void* y, size_t n, cudaStream_t st) {
   unsigned grid = (unsigned)((n + 255) / 256);
   switch (fmt) {
@@ -582,14 +598,8 @@ int launch_decode(int fmt, const void* x, float* y, size_t n, cudaStream_t st) {
   return DEFER_OK;
 }
 int launch_copy_act(int fmt, const void* x, void* y, size_t n, cudaStream_t st) {
-  unsigned grid = (unsigned)((n + 255) / 256);
-  switch (fmt) {
-    case FMT_F32: copy_act_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16X2: copy_act_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16: copy_act_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
-    default: set_error("copy: bad fmt"); return DEFER_ERR_INVALID;
-  }
-  DEFER_CUDA(cudaGetLastError());
+  // planes are contiguous ([hi | lo]): a byte copy keeps every (hi, lo) pair exactly as stored
+  DEFER_CUDA(cudaMemcpyAsync(y, x, n * fmt_bytes_per_elem(fmt), cudaMemcpyDeviceToDevice, st));
   return DEFER_OK;
 }
 

@@ -76,7 +76,7 @@ struct Lane {
   std::vector<void*> buf;   // device pointer per plan buffer
   cudaGraphExec_t exec = nullptr;
   cudaGraph_t graph = nullptr;
-  cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+  cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr, join = nullptr;
   float* out_host = nullptr;  // pinned, last stage
   int* status_host = nullptr; // pinned copy of the sticky device status, refreshed every step (last stage)
   float* dense_partial = nullptr;
@@ -100,7 +100,7 @@ struct defer_stage_s {
   size_t arena_bytes = 0, slot_stride = 0;
   std::vector<void*> workspace;        // everything else we cudaMalloc'ed
   // links
-  bool has_prod = false, has_cons = false, finalized = false;
+  bool has_prod = false, has_cons = false, finalized = false, unlinked = false;
   uint8_t* cons_arena = nullptr;       // consumer arena mapped here (slots + ready flags)
   size_t cons_off_slots = 0, cons_slot_stride = 0;
   uint8_t* prod_arena = nullptr;       // producer arena mapped here (free flags)
@@ -110,6 +110,7 @@ struct defer_stage_s {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   size_t max_dense_partial = 0;
+  cudaEvent_t job_t0 = nullptr, job_t1 = nullptr;
 
   uint32_t* ctrl_u32(size_t off) { return reinterpret_cast<uint32_t*>(arena + off); }
   uint32_t* ready_flag(int d) { return ctrl_u32(OFF_READY + d * FLAG_STRIDE); }
@@ -494,6 +495,7 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
     Lane& L = s->lanes[l];
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&L.t0) != cudaSuccess || cudaEventCreate(&L.t1) != cudaSuccess) {
       set_error("stream/event creation failed");
       return fail(DEFER_ERR_CUDA);
@@ -546,6 +548,7 @@ int defer_stage_destroy(defer_stage_t s) {
     if (L.graph) cudaGraphDestroy(L.graph);
     if (L.stream) cudaStreamDestroy(L.stream);
     if (L.done) cudaEventDestroy(L.done);
+    if (L.join) cudaEventDestroy(L.join);
     if (L.t0) cudaEventDestroy(L.t0);
     if (L.t1) cudaEventDestroy(L.t1);
     for (auto& ua : L.umma) umma_conv_unbind(&ua);
@@ -559,6 +562,8 @@ int defer_stage_destroy(defer_stage_t s) {
   for (void* p : s->d_weights_bf16) if (p) cudaFree(p);
   if (s->cons_arena && s->cons_is_ipc) cudaIpcCloseMemHandle(s->cons_arena);
   if (s->prod_arena && s->prod_is_ipc) cudaIpcCloseMemHandle(s->prod_arena);
+  if (s->job_t0) cudaEventDestroy(s->job_t0);
+  if (s->job_t1) cudaEventDestroy(s->job_t1);
   if (s->flush_buf) cudaFree(s->flush_buf);
   if (s->arena) cudaFree(s->arena);
   delete s;
@@ -699,6 +704,19 @@ int defer_stage_import_link(defer_stage_t s, int role, const void* token) {
   return apply_token(s, role, &t, mapped, is_ipc);
 }
 
+int defer_stage_unlink(defer_stage_t s) {
+  DEFER_CHECK(s, "unlink: null");
+  DEFER_TRY(set_device(s));
+  DEFER_CUDA(cudaDeviceSynchronize());
+  if (s->cons_arena && s->cons_is_ipc) DEFER_CUDA(cudaIpcCloseMemHandle(s->cons_arena));
+  if (s->prod_arena && s->prod_is_ipc) DEFER_CUDA(cudaIpcCloseMemHandle(s->prod_arena));
+  s->cons_arena = nullptr;
+  s->prod_arena = nullptr;
+  s->cons_is_ipc = s->prod_is_ipc = false;
+  s->unlinked = true;
+  return DEFER_OK;
+}
+
 int defer_stage_finalize(defer_stage_t s) {
   DEFER_CHECK(s, "finalize: null");
   DEFER_CHECK(!s->finalized, "finalize: already done");
@@ -753,6 +771,7 @@ int defer_stage_submit(defer_stage_t s, uint64_t seq, const void* host_in, uint6
 int defer_stage_step(defer_stage_t s, uint64_t seq) {
   DEFER_CHECK(s, "step: null");
   DEFER_CHECK(s->finalized, "step: call defer_stage_finalize first");
+  DEFER_CHECK(!s->unlinked, "step: stage was unlinked");
   DEFER_TRY(set_device(s));
   int lane = (int)(seq % s->cfg.depth);
   Lane& L = s->lanes[lane];
@@ -822,6 +841,32 @@ int defer_stage_last_step_us(defer_stage_t s, int lane, float* us) {
   float ms = 0.f;
   DEFER_CUDA(cudaEventElapsedTime(&ms, L.t0, L.t1));
   *us = ms * 1000.f;
+  return DEFER_OK;
+}
+
+int defer_stage_timer_start(defer_stage_t s) {
+  DEFER_CHECK(s, "timer_start: null");
+  DEFER_TRY(set_device(s));
+  if (!s->job_t0) {
+    DEFER_CUDA(cudaEventCreate(&s->job_t0));
+    DEFER_CUDA(cudaEventCreate(&s->job_t1));
+  }
+  DEFER_CUDA(cudaEventRecord(s->job_t0, s->lanes[0].stream));
+  return DEFER_OK;
+}
+
+int defer_stage_timer_stop(defer_stage_t s, float* ms) {
+  DEFER_CHECK(s && ms, "timer_stop: null");
+  DEFER_CHECK(s->job_t0, "timer_stop: timer_start was not called");
+  DEFER_TRY(set_device(s));
+  cudaStream_t s0 = s->lanes[0].stream;
+  for (size_t l = 1; l < s->lanes.size(); ++l) {
+    DEFER_CUDA(cudaEventRecord(s->lanes[l].join, s->lanes[l].stream));
+    DEFER_CUDA(cudaStreamWaitEvent(s0, s->lanes[l].join, 0));
+  }
+  DEFER_CUDA(cudaEventRecord(s->job_t1, s0));
+  DEFER_CUDA(cudaEventSynchronize(s->job_t1));
+  DEFER_CUDA(cudaEventElapsedTime(ms, s->job_t0, s->job_t1));
   return DEFER_OK;
 }
 

@@ -132,6 +132,9 @@ class StageRunner:
         A.check(self.lib.defer_stage_finalize(self.handle))
         self.finalized = True
 
+    def unlink(self) -> None:
+        A.check(self.lib.defer_stage_unlink(self.handle))
+
     # ---- steady state
     def submit(self, seq: int, x: np.ndarray) -> None:
         """Enqueue the H2D copy of microbatch ``seq``.  ``x`` must stay alive and unmodified until the
@@ -210,6 +213,15 @@ class StageRunner:
         A.check(self.lib.defer_stage_op_info(self.handle, op_index, C.byref(b), C.byref(f), name, 128))
         return {"alg_bytes": b.value, "alg_flops": f.value, "kernel": name.value.decode(),
                 "layers": list(self.plan.ops[op_index].layers)}
+
+    def timer_start(self) -> None:
+        A.check(self.lib.defer_stage_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        """Device time (ms) from timer_start to the completion of everything enqueued on all lanes."""
+        ms = C.c_float(0)
+        A.check(self.lib.defer_stage_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
 
     def arm_timing(self, lane: int = 0) -> None:
         us = C.c_float(0)
@@ -307,33 +319,35 @@ class Node:
         ctx.exchange_links(runner)
         runner.finalize()
         ctx.ack_ready()                                 # src/node.py:41-42 (the 0x06 acknowledgement)
-        try:
-            self._data_loop(runner)
-        finally:
-            ctx.barrier()
-            runner.close()
+        self._data_loop(runner)
+        # teardown is the launcher's job (DistContext.shutdown): unlink on every rank, barrier, destroy -
+        # no collective is issued from this thread once the pipeline is up.
 
     def _data_loop(self, runner: StageRunner):
+        """``_data_client`` (src/node.py:103-108): one graph launch per microbatch.  The wait for the
+        input is on the device (ready flag); the host only needs to know how many microbatches exist."""
         ctx = self.ctx
-        rank, world = ctx.rank, ctx.world
-        enq = 0
-        retired = 0
-        is_last = rank == world - 1
+        is_first, is_last = ctx.rank == 0, ctx.rank == ctx.world - 1
+        enq = retired = 0
         out = np.empty(runner.out_shape, np.float32) if is_last else None
         while True:
+            stop = ctx.stop_requested()
             submitted = ctx.submitted()
             progressed = False
-            if rank != 0:  # stage 0 is stepped by the dispatcher's feeder thread in the same process
+            if is_first:
+                enq = submitted            # stage 0 is stepped by the dispatcher's feeder (same process)
+            else:
                 while enq < submitted and (not is_last or enq - retired < runner.depth):
                     runner.step(enq)
                     enq += 1
                     progressed = True
-            if is_last and rank != 0 and retired < enq:
+            if is_last and not is_first and retired < enq:
                 runner.result(retired, out)
                 ctx.publish_result(retired, out)
                 retired += 1
                 progressed = True
-            if ctx.stop_requested() and (rank == 0 or (enq >= ctx.submitted() and retired >= enq or not is_last and enq >= ctx.submitted())):
+            if stop and enq >= ctx.submitted() and (is_first or not is_last or retired >= enq):
                 break
             if not progressed:
                 time.sleep(self.poll_s)
+        runner.sync()

@@ -138,6 +138,10 @@ DEFER_API int defer_stage_link(defer_stage_t prod, defer_stage_t cons);
  * 1 = "my output side" (give to my consumer). */
 DEFER_API int defer_stage_export_link(defer_stage_t s, int role, void* token /* DEFER_LINK_TOKEN_BYTES */);
 DEFER_API int defer_stage_import_link(defer_stage_t s, int role, const void* token);
+/* Drop the mappings of the neighbours' arenas (CUDA-IPC close).  In a multi-process pipeline every rank
+ * calls this, then all ranks synchronise, then each destroys its stage - so no arena is freed while a
+ * neighbour still maps it.  The stage cannot step afterwards. */
+DEFER_API int defer_stage_unlink(defer_stage_t s);
 /* Finish wiring: builds the per-lane CUDA graphs.  Must be called once after linking (also for
  * a single-stage pipeline). */
 DEFER_API int defer_stage_finalize(defer_stage_t s);
@@ -156,6 +160,12 @@ DEFER_API int defer_stage_sync(defer_stage_t s);
 DEFER_API int defer_stage_status(defer_stage_t s);
 /* Device time of the last completed step on `lane` in microseconds (CUDA events on the lane's stream). */
 DEFER_API int defer_stage_last_step_us(defer_stage_t s, int lane, float* us);
+
+/* Whole-job device timing across all lanes (CUDA events, no host clock): start records T0 on lane 0's
+ * stream (call it when the stage is idle, right before the first step of the timed region); stop makes
+ * lane 0 wait for every lane, records T1, synchronises and returns T1 - T0 in milliseconds. */
+DEFER_API int defer_stage_timer_start(defer_stage_t s);
+DEFER_API int defer_stage_timer_stop(defer_stage_t s, float* ms);
 
 /* ---- introspection for tests and benches --------------------------------------------------- */
 DEFER_API int defer_stage_num_kernels(defer_stage_t s, int* per_step);           /* kernel launches per step */
