@@ -44,6 +44,7 @@ struct KParams {
   int cblocks;                                    // cin / 64
   int k_blocks;                                   // taps * cblocks
   int splits;
+  int stages;
   uint32_t flags;
   const float* scale;
   const float* shift;
@@ -159,27 +160,30 @@ struct SmemLayout {
   static constexpr int A_PLANE = BM * 128;          // bytes
   static constexpr int B_PLANE = BN * 128;
   static constexpr int STAGE = NPLANES * (A_PLANE + B_PLANE);
-  static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
-  static constexpr int BAR_OFF = STAGES * STAGE;    // full[STAGES], empty[STAGES], tmem_full, tmem slot
-  static constexpr int SCALE_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = SCALE_OFF + 2 * BN * 4 + 1024;  // + slack for the 1024-B alignment
+  static constexpr int MAX_STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
+  // layout for a run-time ring depth `stages`: [stages x STAGE | barriers 256 B | scale, shift]
+  __host__ __device__ static constexpr int bar_off(int stages) { return stages * STAGE; }
+  __host__ __device__ static constexpr int scale_off(int stages) { return stages * STAGE + 256; }
+  // + slack for the manual 1024-B alignment of the dynamic smem base
+  __host__ __device__ static constexpr int total(int stages) { return stages * STAGE + 256 + 2 * BN * 4 + 1024; }
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
 template <int NPLANES, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
                  const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, const KParams p) {
   using L = SmemLayout<NPLANES, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  const int STAGES = p.stages;                      // ring depth chosen per launch (smem footprint <-> CTAs per SM)
+  const uint32_t bar_base = smem_base + L::bar_off(STAGES);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * L::STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (2 * L::STAGES + 1));
-  float* s_scale = reinterpret_cast<float*>(smem + L::SCALE_OFF);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar_off(STAGES) + 8 * (2 * STAGES + 1));
+  float* s_scale = reinterpret_cast<float*>(smem + L::scale_off(STAGES));
   float* s_shift = s_scale + BN;
   __shared__ int s_is_last;
 
@@ -216,7 +220,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       prefetch_tmap(&tmx1);
       prefetch_tmap(&tmw1);
     }
-    for (int s = 0; s < L::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -275,7 +279,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
           tma_load_4d(a_dst + L::A_PLANE, &tmx1, full_bar(stage), cb * BK, cw, ch, cn);
           tma_load_3d(b_dst + L::B_PLANE, &tmw1, full_bar(stage), cb * BK, c_base, tap);
         }
-        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -305,7 +309,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
           accum = 1;
         }
         umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
-        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full_bar);          // accumulator complete
     }
@@ -329,6 +333,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
       pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
     }
+    // the residual does not depend on the MMAs: fetch chunk 0 while the main loop is still running
+    // (only on the direct path; with split-K the finishing CTA is not known yet)
+    const __nv_bfloat16* rbase =
+        (p.res && valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + c_base : nullptr;
+    uint4 rh[4], rl[4];
+    auto load_res = [&](int c0) {           // residual of one 32-channel chunk: 64 B per plane
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rh[q] = *reinterpret_cast<const uint4*>(rbase + c0 + q * 8);
+        if (NPLANES == 2) rl[q] = *reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + q * 8);
+      }
+    };
+    const bool res_prefetched = rbase != nullptr && p.splits == 1;
+    if (res_prefetched) load_res(0);
     mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -387,24 +405,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
           for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
         }
         if (!valid) continue;
-        const int c = c_base + c0;
-        const size_t o = pix * p.cout + c;
+        const size_t o = pix * p.cout + c_base + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], s_scale[c0 + j], s_shift[c0 + j]);
-        if (p.res) {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + o;
+        if (rbase) {
+          if (c0 == 0 && !res_prefetched) load_res(0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 h = *reinterpret_cast<const uint4*>(rp + q * 8);
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rh[q]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               acc[q * 8 + 2 * e] += __low2float(hh[e]);
               acc[q * 8 + 2 * e + 1] += __high2float(hh[e]);
             }
             if (NPLANES == 2) {
-              uint4 l = *reinterpret_cast<const uint4*>(rp + p.plane_out + q * 8);
-              const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&l);
+              const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&rl[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 acc[q * 8 + 2 * e] += __low2float(ll[e]);
@@ -412,6 +427,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
               }
             }
           }
+          if (c0 + 32 < BN) load_res(c0 + 32);   // next chunk's residual is in flight during this chunk's stores
         }
         if (relu) {
 #pragma unroll
@@ -508,12 +524,16 @@ int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams&
   int dev = 0;
   DEFER_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::total(L::MAX_STAGES)));
     attr_set[dev] = true;
   }
+  int stages = kp.stages < 1 ? 1 : (kp.stages > L::MAX_STAGES ? L::MAX_STAGES : kp.stages);
+  KParams kq = kp;
+  kq.stages = stages;
   dim3 grid(plan.tiles_n * plan.tiles_h * plan.tiles_w, plan.cout / BN, plan.splits);
-  conv_umma_kernel<NPLANES, BN><<<grid, NUM_THREADS, L::TOTAL, st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
-                                                                    plan.tmap_w[NPLANES - 1], kp);
+  conv_umma_kernel<NPLANES, BN><<<grid, NUM_THREADS, L::total(stages), st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
+                                                                    plan.tmap_w[NPLANES - 1], kq);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -582,28 +602,37 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
   }
   const int m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
 
-  // ---- N tile and split-K: aim for >= ~1 wave of 148 SMs without shredding K
-  P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= 148) ? 128 : 64;
+  // ---- N tile, split-K and ring depth.
+  // At batch 1 every conv is latency-bound, and with several microbatches in flight the GPU is bound by
+  // CTA-slot time (sum over launches of CTAs x duration / SMs).  So: fat tiles (BN = 128), split-K only
+  // when a launch would otherwise have a handful of CTAs, and a shallow smem ring for short K loops so
+  // that 2-4 CTAs share an SM and overlap each other's latencies.
+  P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= env_int("DEFER_UMMA_BN128_MIN_CTAS", 8)) ? 128 : 64;
   int force_bn = env_int("DEFER_UMMA_BN", 0);
   if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) P.bn = force_bn;
   int ctas = m_tiles * (cout / P.bn);
   P.splits = 1;
-  int want_split = env_int("DEFER_UMMA_SPLITK", 1);
-  if (want_split && ctas < 96 && P.k_blocks >= 8) {
-    int s = (148 + ctas - 1) / ctas;
+  int target = env_int("DEFER_UMMA_TARGET_CTAS", 16);
+  if (env_int("DEFER_UMMA_SPLITK", 1) && ctas < target && P.k_blocks >= 8) {
+    int s = (target + ctas - 1) / ctas;
     int max_s = P.k_blocks / 4;          // keep >= 4 k-blocks (256 K elements) per split
     if (s > max_s) s = max_s;
-    if (s > 32) s = 32;
+    if (s > 16) s = 16;
     if (s < 1) s = 1;
-    // make every split non-empty
-    int per = (P.k_blocks + s - 1) / s;
-    s = (P.k_blocks + per - 1) / per;
-    P.splits = s;
+    int per = (P.k_blocks + s - 1) / s;  // make every split non-empty
+    P.splits = (P.k_blocks + per - 1) / per;
   }
   int force_split = env_int("DEFER_UMMA_FORCE_SPLITS", 0);
   if (force_split > 0 && force_split <= P.k_blocks) {
     int per = (P.k_blocks + force_split - 1) / force_split;
     P.splits = (P.k_blocks + per - 1) / per;
+  }
+  {
+    int kb_per = (P.k_blocks + P.splits - 1) / P.splits;
+    int st = kb_per <= 2 ? kb_per : (kb_per <= 6 ? 2 : 4);
+    int force_st = env_int("DEFER_UMMA_STAGES", 0);
+    if (force_st > 0) st = force_st;
+    P.stages = st;
   }
 
   // ---- weights: fp32 HWIO -> bf16 [plane][tap][cout][cin]
@@ -680,6 +709,7 @@ int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStrea
   kp.cblocks = P.cin / 64;
   kp.k_blocks = P.k_blocks;
   kp.splits = P.splits;
+  kp.stages = P.stages;
   kp.flags = P.flags;
   kp.scale = P.scale; kp.shift = P.shift;
   kp.res = (P.flags & DEFER_FLAG_RESIDUAL) ? a.res : nullptr;

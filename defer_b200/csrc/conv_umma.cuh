@@ -19,7 +19,7 @@ struct UmmaConvPlan {
   int bn = 64;             // N tile (cout per CTA)
   int k_blocks = 0;        // taps * cin / 64
   int splits = 1;          // split-K factor (grid.z)
-  int stages = 4;
+  int stages = 4;          // smem ring depth (run-time: fewer stages -> more CTAs per SM)
   size_t smem_bytes = 0;
   void* w_dev = nullptr;   // transformed weights
   const float* scale = nullptr;
