@@ -191,6 +191,7 @@ def workload_config(args, depth):
     return {"workload": f"{args.model} {args.gpus}-stage pipeline, batch {args.batch}, 224x224x3 synthetic image, "
                         f"{'fp32 parity path (bf16x3 on tcgen05)' if args.dtype == 'float32' else args.dtype}",
             "model": args.model, "stages": args.gpus, "batch": args.batch, "depth": depth,
+            "max_inflight": None if depth is None else depth * args.gpus,
             "parallelism": f"pp{args.gpus}",
             "l2": "not flushed between steps: steady-state pipeline re-reads the same weights every microbatch by "
                   "design; the per-kernel roofline numbers are taken with a 256 MB L2 flush between launches"}
@@ -213,13 +214,13 @@ def run_b200(args):
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus}")
         args.gpus = world
     n_stages = args.gpus
-    depth = args.depth or (8 if n_stages == 1 else 6)
+    depth = args.depth or 16
     K, W, B = args.steps, max(args.warmup, 3), args.batch
 
     ctx = None
     if world > 1:
         from defer_b200.dist import DistContext
-        ctx = DistContext(ring=max(64, 2 * depth), out_elems=1000, batch=B)
+        ctx = DistContext(ring=max(64, 4 * depth * world), out_elems=1000, batch=B)
     torch.cuda.set_device(local_rank)
 
     model = build_model(args.model) if rank == 0 else None
@@ -228,7 +229,8 @@ def run_b200(args):
 
     # ---- build the pipeline through the public pieces (DEFER partition + dispatch)
     defer = DEFER(list(range(n_stages)), dtype=args.dtype, depth=depth, batch=B, conv_backend=args.conv_backend, dist=ctx)
-    in_q, out_q = queue.Queue(depth), queue.Queue(4 * depth)
+    max_inflight = depth * (world if ctx is not None else 1)
+    in_q, out_q = queue.Queue(max_inflight), queue.Queue(4 * max_inflight)
     node_thread = None
     if ctx is not None:
         node = Node(dist_ctx=ctx, device=local_rank)
@@ -317,7 +319,7 @@ def run_b200(args):
         # one process per GPU: rank 0 steps stage 0 and publishes `submitted`; node loops follow
         if rank == 0:
             for s in range(start, start + n):
-                while s - ctx.done() >= depth:
+                while s - ctx.done() >= max_inflight:
                     pass
                 runner.step(s)
                 ctx.mark_submitted(s + 1)

@@ -1,4 +1,6 @@
 // api_kernels.cu - per-kernel C-ABI entry points (raw device pointers) for parity tests and ncu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_umma.cuh"
 
@@ -23,8 +25,35 @@ int defer_k_conv(int fmt, int backend, const void* x, int x_is_f32, const float*
     UmmaConvLaneArgs args;
     int rc = umma_conv_prepare(&plan, fmt, n, h, w, cin, ho, wo, cout, kh, kw, sh, sw, pad_t, pad_l, flags, w_hwio, scale, shift);
     if (rc == DEFER_OK) rc = umma_conv_bind(plan, &args, x, residual, y);
+    long long* trace = nullptr;
+    int n_ctas = plan.tiles_n * plan.tiles_h * plan.tiles_w * (plan.cout / plan.bn) * plan.splits;
+    const char* trace_path = getenv("DEFER_UMMA_TRACE");
+    if (rc == DEFER_OK && trace_path) {
+      cudaMalloc((void**)&trace, (size_t)n_ctas * 8 * sizeof(long long));
+      cudaMemset(trace, 0, (size_t)n_ctas * 8 * sizeof(long long));
+      args.trace = trace;
+      rc = launch_conv_umma(plan, args, st);   // warm-up launch (descriptor / instruction caches)
+      cudaStreamSynchronize(st);
+    }
     if (rc == DEFER_OK) rc = launch_conv_umma(plan, args, st);
     cudaError_t e = cudaStreamSynchronize(st);
+    if (trace) {
+      long long* h = (long long*)malloc((size_t)n_ctas * 8 * sizeof(long long));
+      cudaMemcpy(h, trace, (size_t)n_ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+      FILE* f = fopen(trace_path, "a");
+      if (f) {
+        fprintf(f, "# conv n=%d h=%d w=%d cin=%d cout=%d k=%d s=%d bn=%d splits=%d stages=%d ctas=%d\n", n, h, w, cin, cout, kh, sh,
+                plan.bn, plan.splits, plan.stages, n_ctas);
+        for (int i = 0; i < n_ctas; ++i) {
+          long long* t = h + 8 * i;
+          fprintf(f, "%d %lld %lld %lld %lld %lld %lld %lld\n", i, t[7], t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0],
+                  t[5] - t[0], t[6] - t[0]);
+        }
+        fclose(f);
+      }
+      free(h);
+      cudaFree(trace);
+    }
     umma_conv_unbind(&args);
     umma_conv_release(plan);
     if (rc != DEFER_OK) return rc;

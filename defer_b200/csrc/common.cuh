@@ -40,6 +40,16 @@ const char* get_error();
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Every kernel of the library asks for the same (maximum) shared-memory carve-out.  Lanes run
+// concurrently on one GPU; CTAs of kernels that want different L1/shared splits cannot share an SM, and
+// switching the split drains it.  One uniform configuration lets tiny SIMT kernels and 200 KB tcgen05
+// tiles co-reside.  Called once per (kernel, device).
+// ---------------------------------------------------------------------------------------------
+void prefer_max_smem_impl(const void* func);
+template <class K>
+inline void prefer_max_smem(K kernel) { prefer_max_smem_impl(reinterpret_cast<const void*>(kernel)); }
+
+// ---------------------------------------------------------------------------------------------
 // activation formats (defer_fmt).  BF16X2 stores v as hi = bf16(v), lo = bf16(v - hi) in two planes:
 // hi plane at element offset 0, lo plane at element offset `plane` (= total elements of the tensor).
 // ---------------------------------------------------------------------------------------------

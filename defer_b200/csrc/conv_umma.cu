@@ -20,6 +20,7 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv_umma.cuh"
@@ -54,6 +55,7 @@ struct KParams {
   unsigned int* counters;
   size_t plane_out;                               // n*ho*wo*cout (elements) - offset of the lo plane
   int* error_flag;
+  long long* trace;   // optional: 8 clock64 stamps per CTA (debug instrumentation)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -189,6 +191,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* trace = p.trace ? p.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  if (trace && threadIdx.x == 0) { trace[0] = clock64(); trace[7] = (long long)gtimer(); }
 
   // ---- tile coordinates
   const int tile_id = blockIdx.x;
@@ -245,6 +249,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();   // setup done
 
   if (warp == 0) {
     // =================================================================== TMA producer
@@ -291,6 +296,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       uint32_t accum = 0;
       for (int i = 0; i < num_kb; ++i) {
         mbar_wait(full_bar(stage), phase, p.error_flag, 2);
+        if (trace && i == 0) trace[2] = clock64();           // first operands landed
         tc_fence_after();
         const uint32_t a_addr = smem_base + stage * L::STAGE;
         const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
@@ -312,6 +318,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full_bar);          // accumulator complete
+      if (trace) trace[3] = clock64();                     // all MMAs issued
     }
   } else {
     // =================================================================== epilogue (warps 2..5)
@@ -348,6 +355,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     const bool res_prefetched = rbase != nullptr && p.splits == 1;
     if (res_prefetched) load_res(0);
     mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
+    if (trace && threadIdx.x == 64) trace[4] = clock64();   // accumulator visible to the epilogue
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool relu = p.flags & DEFER_FLAG_RELU;
@@ -455,13 +463,321 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   }
 
   // ---- teardown
+  if (trace && threadIdx.x == 64) trace[5] = clock64();     // epilogue stores issued
   tc_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 0) trace[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     constexpr uint32_t ncols = BN < 32 ? 32 : BN;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
+}
+
+// ==============================================================================================
+// Stage megakernel: a RUN of consecutive convolutions executed by ONE launch.
+//
+// At batch 1 every ResNet conv is a handful of 128-row tiles and a kernel launch (+ the dependency
+// latency between dependent launches) costs more than the tile itself; 52 launches per inference also
+// hit the device-wide launch rate when several microbatches are in flight.  Here one thread-block
+// CLUSTER (hardware co-scheduled, <= 16 CTAs) walks the whole op list: the tiles of an op are dealt
+// round-robin to the CTAs of the cluster, a hardware cluster barrier (barrier.cluster, release/acquire)
+// separates dependent ops, and barriers / TMEM / descriptors are set up once.  The warp roles of the
+// per-op kernel are kept and run continuously across tiles and ops:
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 epilogue, with TWO TMEM accumulators so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+// Lanes (microbatches in flight) run one cluster each, concurrently.
+// ==============================================================================================
+struct alignas(128) MegaOp {
+  CUtensorMap tmx[2];
+  CUtensorMap tmw[2];
+  KParams p;
+  int m_tiles, n_tiles;     // tiles of this op: m fastest
+  int pad_[2];
+};
+
+constexpr int MEGA_BN = 64;
+constexpr int MEGA_ACC_BUFS = 2;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int NPLANES>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_cluster, int* error_flag) {
+  constexpr int BN = MEGA_BN;
+  using L = SmemLayout<NPLANES, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int STAGES = stages;
+  const uint32_t bar_base = smem_base + L::bar_off(STAGES);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + MEGA_ACC_BUFS + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar_off(STAGES) + 8 * (2 * STAGES + 2 * MEGA_ACC_BUFS));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // cluster mode: one cluster walks a chain of dependent ops.  grid mode (n_ops == 1): a plain persistent
+  // grid deals the tiles of ONE op round-robin - no inter-CTA dependency, no cluster barrier.
+  const int rank = use_cluster ? (int)cluster_ctarank() : (int)blockIdx.x;
+  const int csize = use_cluster ? (int)cluster_nctarank() : (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < MEGA_ACC_BUFS; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);      // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    constexpr uint32_t ncols = MEGA_ACC_BUFS * BN;   // 128
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // running pipeline state of each role (every role walks the same (op, tile, k-block) sequence)
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t it = 0;   // tiles processed by this CTA so far -> accumulator buffer / phase
+
+  for (int oi = 0; oi < n_ops; ++oi) {
+    const MegaOp& op = ops[oi];
+    const KParams& p = op.p;
+    const int n_tiles = op.m_tiles * op.n_tiles;
+    if (oi > 0) {
+      // dependent op: everything the cluster stored must be visible (also to the TMA / async proxy)
+      asm volatile("fence.proxy.async;" ::: "memory");
+      cluster_sync_all();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (warp == 0) {
+      // =================================================================== TMA producer
+      if (lane == 0) {
+        prefetch_tmap(&op.tmx[0]);
+        prefetch_tmap(&op.tmw[0]);
+        const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
+        const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
+        for (int tile = rank; tile < n_tiles; tile += csize) {
+          const int mt = tile % op.m_tiles, nt = tile / op.m_tiles;
+          int n0 = 0, h0 = 0, w0 = 0;
+          if (p.flat) {
+            w0 = mt * BM;
+          } else {
+            int tw = mt % p.tiles_w;
+            int t2 = mt / p.tiles_w;
+            n0 = (t2 / p.tiles_h) * p.tile_n;
+            h0 = (t2 % p.tiles_h) * p.tile_h;
+            w0 = tw * p.tile_w;
+          }
+          const int c_base = nt * BN;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 11);
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int khi = tap / p.kw;
+            const int kwi = tap - khi * p.kw;
+            const uint32_t a_dst = smem_base + stage * L::STAGE;
+            const uint32_t b_dst = a_dst + NPLANES * L::A_PLANE;
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            int cw, ch, cn;
+            if (p.flat) {
+              cw = w0; ch = 0; cn = 0;
+            } else {
+              cw = w0 * p.sw + kwi - p.pad_l;
+              ch = h0 * p.sh + khi - p.pad_t;
+              cn = n0;
+            }
+            tma_load_4d(a_dst, &op.tmx[0], full_bar(stage), cb * BK, cw, ch, cn);
+            tma_load_3d(b_dst, &op.tmw[0], full_bar(stage), cb * BK, c_base, tap);
+            if (NPLANES == 2) {
+              tma_load_4d(a_dst + L::A_PLANE, &op.tmx[1], full_bar(stage), cb * BK, cw, ch, cn);
+              tma_load_3d(b_dst + L::B_PLANE, &op.tmw[1], full_bar(stage), cb * BK, c_base, tap);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();   // reconverge before the (warp-aligned) cluster barrier
+    } else if (warp == 1) {
+      // =================================================================== MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc<BN>();
+        for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+          const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+          mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 12);   // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          uint32_t accum = 0;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(full_bar(stage), phase, error_flag, 13);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * L::STAGE;
+            const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
+              const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));
+              if (NPLANES == 2) {
+                const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
+                const uint64_t b_lo = make_sw128_desc(b_addr + L::B_PLANE + k * (UMMA_K * 2));
+                umma_bf16(tmem_d, a_lo, b_hi, idesc, accum);
+                accum = 1;
+                umma_bf16(tmem_d, a_hi, b_lo, idesc, accum);
+              }
+              umma_bf16(tmem_d, a_hi, b_hi, idesc, accum);
+              accum = 1;
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull_bar(buf));
+        }
+      }
+      __syncwarp();
+    } else {
+      // =================================================================== epilogue (warps 2..5)
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;
+      const bool relu = p.flags & DEFER_FLAG_RELU;
+      for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+        const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+        const int mt = tile % op.m_tiles, nt = tile / op.m_tiles;
+        const int c_base = nt * BN;
+        bool valid;
+        size_t pix;
+        if (p.flat) {
+          int m = mt * BM + r;
+          valid = m < p.m_total;
+          pix = (size_t)m;
+        } else {
+          int tw0 = mt % p.tiles_w;
+          int t2 = mt / p.tiles_w;
+          int n0 = (t2 / p.tiles_h) * p.tile_n, h0 = (t2 % p.tiles_h) * p.tile_h, w0 = tw0 * p.tile_w;
+          int tw = r % p.tile_w;
+          int t3 = r / p.tile_w;
+          int th = t3 % p.tile_h;
+          int tn = t3 / p.tile_h;
+          int nn = n0 + tn, oh = h0 + th, ow = w0 + tw;
+          valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
+          pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
+        }
+        const __nv_bfloat16* rbase =
+            (p.res && valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + c_base : nullptr;
+        uint4 rh[4], rl[4];
+        auto load_res = [&](int c0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rh[q] = *reinterpret_cast<const uint4*>(rbase + c0 + q * 8);
+            if (NPLANES == 2) rl[q] = *reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + q * 8);
+          }
+        };
+        if (rbase) load_res(0);
+        mbar_wait(tfull_bar(buf), aphase, error_flag, 14);
+        tc_fence_after();
+        const uint32_t taddr_row = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr_row + c0, v);
+          if (c0 + 32 >= BN) {
+            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          if (!valid) continue;
+          float acc[32];
+          const int c = c_base + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float sc = p.scale ? __ldg(p.scale + c + j) : 1.f;
+            float sf = p.shift ? __ldg(p.shift + c + j) : 0.f;
+            acc[j] = fmaf(__uint_as_float(v[j]), sc, sf);
+          }
+          if (rbase) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rh[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[q * 8 + 2 * e] += __low2float(hh[e]);
+                acc[q * 8 + 2 * e + 1] += __high2float(hh[e]);
+              }
+              if (NPLANES == 2) {
+                const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&rl[q]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  acc[q * 8 + 2 * e] += __low2float(ll[e]);
+                  acc[q * 8 + 2 * e + 1] += __high2float(ll[e]);
+                }
+              }
+            }
+            if (c0 + 32 < BN) load_res(c0 + 32);
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+          }
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.cout + c;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 h, l;
+            uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+            uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (NPLANES == 2) {
+                split_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1], hp[e], lp[e]);
+              } else {
+                hp[e] = pack_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+              }
+            }
+            *reinterpret_cast<uint4*>(yp + q * 8) = h;
+            if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + q * 8) = l;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    constexpr uint32_t ncols = MEGA_ACC_BUFS * BN;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+  // no CTA may exit while a peer could still be inside a cluster barrier
+  if (use_cluster) cluster_sync_all();
 }
 
 // weights: fp32 HWIO [tap][cin][cout]  ->  bf16 [plane][tap][cout][cin]
@@ -526,6 +842,7 @@ int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams&
   if (dev < 64 && !attr_set[dev]) {
     DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::total(L::MAX_STAGES)));
+    prefer_max_smem(conv_umma_kernel<NPLANES, BN>);
     attr_set[dev] = true;
   }
   int stages = kp.stages < 1 ? 1 : (kp.stages > L::MAX_STAGES ? L::MAX_STAGES : kp.stages);
@@ -560,7 +877,7 @@ static int env_int(const char* name, int dflt) {
 
 int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
                       int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
-                      const float* shift_dev) {
+                      const float* shift_dev, bool mega) {
   UmmaConvPlan& P = *plan;
   P = UmmaConvPlan();
   P.fmt = fmt;
@@ -627,6 +944,10 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
     int per = (P.k_blocks + force_split - 1) / force_split;
     P.splits = (P.k_blocks + per - 1) / per;
   }
+  if (mega) {   // megakernel tiles: one N-tile width, the whole K loop inside the tile
+    P.bn = MEGA_BN;
+    P.splits = 1;
+  }
   {
     int kb_per = (P.k_blocks + P.splits - 1) / P.splits;
     int st = kb_per <= 2 ? kb_per : (kb_per <= 6 ? 2 : 4);
@@ -640,6 +961,7 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
   DEFER_CUDA(cudaMalloc(&P.w_dev, welems * 2 * P.nplanes));
   {
     unsigned grid = (unsigned)((welems + 255) / 256);
+    prefer_max_smem(weight_transform_kernel);
     weight_transform_kernel<<<grid, 256>>>(w_hwio_dev, (__nv_bfloat16*)P.w_dev, taps, cin, cout, P.nplanes);
     DEFER_CUDA(cudaGetLastError());
   }
@@ -699,8 +1021,8 @@ void umma_conv_unbind(UmmaConvLaneArgs* a) {
   a->counters = nullptr;
 }
 
-int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStream_t st) {
-  KParams kp;
+static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KParams* out) {
+  KParams& kp = *out;
   kp.n = P.n; kp.ho = P.ho; kp.wo = P.wo; kp.cout = P.cout;
   kp.tile_n = P.tile_n; kp.tile_h = P.tile_h; kp.tile_w = P.tile_w; kp.tiles_h = P.tiles_h; kp.tiles_w = P.tiles_w;
   kp.flat = P.flat;
@@ -718,8 +1040,120 @@ int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStrea
   kp.counters = a.counters;
   kp.plane_out = (size_t)P.n * P.ho * P.wo * P.cout;
   kp.error_flag = nullptr;
+  kp.trace = a.trace;
+}
+
+int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStream_t st) {
+  KParams kp;
+  fill_kparams(P, a, &kp);
   if (P.nplanes == 2) return P.bn == 128 ? launch_t<2, 128>(P, a, kp, st) : launch_t<2, 64>(P, a, kp, st);
   return P.bn == 128 ? launch_t<1, 128>(P, a, kp, st) : launch_t<1, 64>(P, a, kp, st);
+}
+
+// ---- megakernel host side
+size_t umma_mega_op_bytes() { return sizeof(MegaOp); }
+
+int umma_mega_fill(void* host_dst, const UmmaConvPlan& P, const UmmaConvLaneArgs& a) {
+  if (!P.ready || P.bn != MEGA_BN || P.splits != 1) {
+    set_error("umma_mega_fill: plan is not a megakernel plan (bn %d, splits %d)", P.bn, P.splits);
+    return DEFER_ERR_STATE;
+  }
+  MegaOp op;
+  memset(&op, 0, sizeof op);
+  op.tmx[0] = a.tmap_x[0];
+  op.tmx[1] = a.tmap_x[1];
+  op.tmw[0] = P.tmap_w[0];
+  op.tmw[1] = P.tmap_w[1];
+  fill_kparams(P, a, &op.p);
+  op.m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
+  op.n_tiles = P.cout / MEGA_BN;
+  memcpy(host_dst, &op, sizeof op);
+  return DEFER_OK;
+}
+
+int umma_mega_cluster_size() {
+  static int cached = 0;
+  if (cached) return cached;
+  int want = env_int("DEFER_MEGA_CLUSTER", 16);
+  if (want < 1) want = 1;
+  if (want > 16) want = 16;
+  cached = want;
+  return cached;
+}
+
+template <int NPLANES>
+static int launch_mega_t(const void* dev_ops, int n_ops, int stages, cudaStream_t st) {
+  using L = SmemLayout<NPLANES, MEGA_BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (stages < 1) stages = 1;
+  if (stages > L::MAX_STAGES) stages = L::MAX_STAGES;
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::total(L::MAX_STAGES)));
+    DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    prefer_max_smem(conv_mega_kernel<NPLANES>);
+    attr_set[dev] = true;
+  }
+  const int cluster = umma_mega_cluster_size();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(cluster, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::total(stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const MegaOp* ops = reinterpret_cast<const MegaOp*>(dev_ops);
+  int* err = nullptr;
+  int use_cluster = 1;
+  DEFER_CUDA(cudaLaunchKernelEx(&cfg, conv_mega_kernel<NPLANES>, ops, n_ops, stages, use_cluster, err));
+  return DEFER_OK;
+}
+
+// ONE op on a persistent grid (many tiles: batched microbatches / large feature maps)
+template <int NPLANES>
+static int launch_persist_t(const void* dev_op, int n_tiles, cudaStream_t st) {
+  using L = SmemLayout<NPLANES, MEGA_BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::total(L::MAX_STAGES)));
+    DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    prefer_max_smem(conv_mega_kernel<NPLANES>);
+    attr_set[dev] = true;
+  }
+  static int sms = 0;
+  if (!sms) DEFER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int stages = env_int("DEFER_PERSIST_STAGES", NPLANES == 2 ? 2 : 4);
+  if (stages > L::MAX_STAGES) stages = L::MAX_STAGES;
+  int per_sm = (227 * 1024) / L::total(stages);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  const MegaOp* ops = reinterpret_cast<const MegaOp*>(dev_op);
+  int* err = nullptr;
+  conv_mega_kernel<NPLANES><<<grid, NUM_THREADS, L::total(stages), st>>>(ops, 1, stages, 0, err);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st) {
+  return nplanes == 2 ? launch_persist_t<2>(dev_op, n_tiles, st) : launch_persist_t<1>(dev_op, n_tiles, st);
+}
+
+int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st) {
+  int stages = env_int("DEFER_MEGA_STAGES", 2);   // 2 x 48 KB: two clusters' CTAs share an SM
+  return nplanes == 2 ? launch_mega_t<2>(dev_ops, n_ops, stages, st) : launch_mega_t<1>(dev_ops, n_ops, stages, st);
 }
 
 void umma_conv_release(UmmaConvPlan& P) {

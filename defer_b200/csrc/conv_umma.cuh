@@ -35,16 +35,25 @@ struct UmmaConvLaneArgs {
   void* y = nullptr;
   float* partial = nullptr;          // split-K partial tiles (per lane: lanes run concurrently)
   unsigned int* counters = nullptr;  // split-K arrival counters, one per output tile
+  long long* trace = nullptr;        // debug: per-CTA phase stamps (see DEFER_UMMA_TRACE)
 };
 
 bool umma_conv_supported(int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw, int sh, int sw,
                          int pad_t, int pad_l);
 int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
                       int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
-                      const float* shift_dev);
+                      const float* shift_dev, bool mega = false);
 int umma_conv_bind(const UmmaConvPlan& plan, UmmaConvLaneArgs* args, const void* x, const void* res, void* y);
 void umma_conv_unbind(UmmaConvLaneArgs* args);
 int launch_conv_umma(const UmmaConvPlan& plan, const UmmaConvLaneArgs& args, cudaStream_t st);
 void umma_conv_release(UmmaConvPlan& plan);
+
+// Stage megakernel: a run of consecutive convs in ONE cluster launch (conv_umma.cu, conv_mega_kernel).
+size_t umma_mega_op_bytes();
+int umma_mega_fill(void* host_dst, const UmmaConvPlan& plan, const UmmaConvLaneArgs& args);   // one op descriptor
+int umma_mega_cluster_size();
+int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st);
+// one op on a persistent grid (same kernel, grid mode): for ops with many tiles
+int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st);
 
 }  // namespace defer

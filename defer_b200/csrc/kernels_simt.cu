@@ -180,10 +180,13 @@ template <int FIN, int FOUT>
 static int launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
   int M = p.n * p.ho * p.wo;
   dim3 grid((M + CBM - 1) / CBM, (p.cout + CBN - 1) / CBN);
-  if (p.cin % 4 == 0)
+  if (p.cin % 4 == 0) {
+    prefer_max_smem(conv_simt_kernel<FIN, FOUT, true>);
     conv_simt_kernel<FIN, FOUT, true><<<grid, 256, 0, st>>>(p);
-  else
+  } else {
+    prefer_max_smem(conv_simt_kernel<FIN, FOUT, false>);
     conv_simt_kernel<FIN, FOUT, false><<<grid, 256, 0, st>>>(p);
+  }
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -242,9 +245,9 @@ int launch_maxpool(int fmt, const void* x, void* y, int n, int h, int w, int c, 
   size_t total = (size_t)n * ho * wo * (c / 4);
   unsigned grid = (unsigned)((total + 255) / 256);
   switch (fmt) {
-    case FMT_F32: maxpool_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
-    case FMT_BF16X2: maxpool_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
-    case FMT_BF16: maxpool_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    case FMT_F32: prefer_max_smem(maxpool_kernel<FMT_F32>); maxpool_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16X2: prefer_max_smem(maxpool_kernel<FMT_BF16X2>); maxpool_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16: prefer_max_smem(maxpool_kernel<FMT_BF16>); maxpool_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo); break;
     default: set_error("maxpool: bad fmt"); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -279,9 +282,9 @@ __global__ void __launch_bounds__(256) gap_kernel(const void* __restrict__ x, vo
 int launch_gap(int fmt, const void* x, void* y, int n, int h, int w, int c, cudaStream_t st) {
   dim3 grid((c + 31) / 32, n), block(32, 8);
   switch (fmt) {
-    case FMT_F32: gap_kernel<FMT_F32><<<grid, block, 0, st>>>(x, y, h * w, c); break;
-    case FMT_BF16X2: gap_kernel<FMT_BF16X2><<<grid, block, 0, st>>>(x, y, h * w, c); break;
-    case FMT_BF16: gap_kernel<FMT_BF16><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    case FMT_F32: prefer_max_smem(gap_kernel<FMT_F32>); gap_kernel<FMT_F32><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    case FMT_BF16X2: prefer_max_smem(gap_kernel<FMT_BF16X2>); gap_kernel<FMT_BF16X2><<<grid, block, 0, st>>>(x, y, h * w, c); break;
+    case FMT_BF16: prefer_max_smem(gap_kernel<FMT_BF16>); gap_kernel<FMT_BF16><<<grid, block, 0, st>>>(x, y, h * w, c); break;
     default: set_error("gap: bad fmt"); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -373,10 +376,13 @@ int launch_dense(int fmt, const void* x, const void* w, bool w_is_bf16, const fl
     return DEFER_ERR_INVALID;
   }
 #define DENSE_LAUNCH(FM)                                                                                           \
-  if (w_is_bf16)                                                                                                   \
+  if (w_is_bf16) {                                                                                                 \
+    prefer_max_smem(dense_partial_kernel<FM, __nv_bfloat16>);                                                      \
     dense_partial_kernel<FM, __nv_bfloat16><<<grid, DENSE_TB, smem, st>>>(x, (const __nv_bfloat16*)w, partial, n, F, U, rows); \
-  else                                                                                                             \
-    dense_partial_kernel<FM, float><<<grid, DENSE_TB, smem, st>>>(x, (const float*)w, partial, n, F, U, rows);
+  } else {                                                                                                         \
+    prefer_max_smem(dense_partial_kernel<FM, float>);                                                              \
+    dense_partial_kernel<FM, float><<<grid, DENSE_TB, smem, st>>>(x, (const float*)w, partial, n, F, U, rows);     \
+  }
   switch (fmt) {
     case FMT_F32: DENSE_LAUNCH(FMT_F32); break;
     case FMT_BF16X2: DENSE_LAUNCH(FMT_BF16X2); break;
@@ -389,9 +395,9 @@ int launch_dense(int fmt, const void* x, const void* w, bool w_is_bf16, const fl
   unsigned g2 = (unsigned)((total + 255) / 256);
   int fout = y_is_f32 ? FMT_F32 : fmt;
   switch (fout) {
-    case FMT_F32: dense_reduce_kernel<FMT_F32><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
-    case FMT_BF16X2: dense_reduce_kernel<FMT_BF16X2><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
-    case FMT_BF16: dense_reduce_kernel<FMT_BF16><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+    case FMT_F32: prefer_max_smem(dense_reduce_kernel<FMT_F32>); dense_reduce_kernel<FMT_F32><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+    case FMT_BF16X2: prefer_max_smem(dense_reduce_kernel<FMT_BF16X2>); dense_reduce_kernel<FMT_BF16X2><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
+    case FMT_BF16: prefer_max_smem(dense_reduce_kernel<FMT_BF16>); dense_reduce_kernel<FMT_BF16><<<g2, 256, 0, st>>>(partial, bias, y, n, U, splits, flags); break;
   }
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 }
 
 int launch_softmax(const float* x, float* y, int n, int c, cudaStream_t st) {
-  softmax_kernel<<<n, 256, 0, st>>>(x, y, c);
+  prefer_max_smem(softmax_kernel); softmax_kernel<<<n, 256, 0, st>>>(x, y, c);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -497,9 +503,9 @@ static int launch_eltwise_t(int kind, const void* a, const void* b, const float*
                             size_t n_elems, int c, uint32_t flags, cudaStream_t st) {
   unsigned grid = (unsigned)((n_elems / 4 + 255) / 256);
   switch (kind) {
-    case DEFER_OP_AFFINE: eltwise_kernel<FMT, DEFER_OP_AFFINE><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
-    case DEFER_OP_RELU: eltwise_kernel<FMT, DEFER_OP_RELU><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
-    case DEFER_OP_ADD: eltwise_kernel<FMT, DEFER_OP_ADD><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    case DEFER_OP_AFFINE: prefer_max_smem(eltwise_kernel<FMT, DEFER_OP_AFFINE>); eltwise_kernel<FMT, DEFER_OP_AFFINE><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    case DEFER_OP_RELU: prefer_max_smem(eltwise_kernel<FMT, DEFER_OP_RELU>); eltwise_kernel<FMT, DEFER_OP_RELU><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
+    case DEFER_OP_ADD: prefer_max_smem(eltwise_kernel<FMT, DEFER_OP_ADD>); eltwise_kernel<FMT, DEFER_OP_ADD><<<grid, 256, 0, st>>>(a, b, scale, shift, y, n_elems, c, flags); break;
     default: set_error("eltwise: bad kind %d", kind); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -515,7 +521,7 @@ int launch_eltwise(int fmt, int kind, const void* a, const void* b, const float*
   size_t n_elems = n_pix * (size_t)c;
   if (fmt == FMT_BF16X2 && kind == DEFER_OP_RELU) {
     size_t n_pairs = n_elems / 2;
-    relu_planes_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>((const uint32_t*)a, (uint32_t*)y, n_pairs);
+    prefer_max_smem(relu_planes_kernel); relu_planes_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>((const uint32_t*)a, (uint32_t*)y, n_pairs);
     DEFER_CUDA(cudaGetLastError());
     return DEFER_OK;
   }
@@ -553,9 +559,9 @@ int launch_pad(int fmt, const void* x, void* y, int n, int h, int w, int c, int 
   size_t total = (size_t)n * ho * wo * c;
   unsigned grid = (unsigned)((total + 255) / 256);
   switch (fmt) {
-    case FMT_F32: pad_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
-    case FMT_BF16X2: pad_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
-    case FMT_BF16: pad_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    case FMT_F32: prefer_max_smem(pad_kernel<FMT_F32>); pad_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16X2: prefer_max_smem(pad_kernel<FMT_BF16X2>); pad_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
+    case FMT_BF16: prefer_max_smem(pad_kernel<FMT_BF16>); pad_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n, h, w, c, pad_t, pad_l, ho, wo); break;
     default: set_error("pad: bad fmt"); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -578,9 +584,9 @@ __global__ void __launch_bounds__(256) decode_kernel(const void* __restrict__ x,
 int launch_encode(int fmt, const float* x, void* y, size_t n, cudaStream_t st) {
   unsigned grid = (unsigned)((n + 255) / 256);
   switch (fmt) {
-    case FMT_F32: encode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16X2: encode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16: encode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_F32: prefer_max_smem(encode_kernel<FMT_F32>); encode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16X2: prefer_max_smem(encode_kernel<FMT_BF16X2>); encode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16: prefer_max_smem(encode_kernel<FMT_BF16>); encode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
     default: set_error("encode: bad fmt"); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -589,9 +595,9 @@ int launch_encode(int fmt, const float* x, void* y, size_t n, cudaStream_t st) {
 int launch_decode(int fmt, const void* x, float* y, size_t n, cudaStream_t st) {
   unsigned grid = (unsigned)((n + 255) / 256);
   switch (fmt) {
-    case FMT_F32: decode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16X2: decode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
-    case FMT_BF16: decode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_F32: prefer_max_smem(decode_kernel<FMT_F32>); decode_kernel<FMT_F32><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16X2: prefer_max_smem(decode_kernel<FMT_BF16X2>); decode_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, y, n); break;
+    case FMT_BF16: prefer_max_smem(decode_kernel<FMT_BF16>); decode_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, y, n); break;
     default: set_error("decode: bad fmt"); return DEFER_ERR_INVALID;
   }
   DEFER_CUDA(cudaGetLastError());
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 }
 int launch_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t st) {
   unsigned grid = (unsigned)((n + 255) / 256);
-  f32_to_bf16_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n);
+  prefer_max_smem(f32_to_bf16_kernel); f32_to_bf16_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -663,12 +669,12 @@ __global__ void signal_flag_kernel(uint32_t* remote_flag, uint32_t* counter) {
 
 int launch_wait_flag(const uint32_t* flag, uint32_t* counter, int minus, int* status, unsigned long long timeout_ns,
                      cudaStream_t st) {
-  wait_flag_kernel<<<1, 32, 0, st>>>(flag, counter, minus, status, timeout_ns);
+  prefer_max_smem(wait_flag_kernel); wait_flag_kernel<<<1, 32, 0, st>>>(flag, counter, minus, status, timeout_ns);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
 int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, cudaStream_t st) {
-  signal_flag_kernel<<<1, 32, 0, st>>>(remote_flag, counter);
+  prefer_max_smem(signal_flag_kernel); signal_flag_kernel<<<1, 32, 0, st>>>(remote_flag, counter);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }

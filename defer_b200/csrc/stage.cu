@@ -12,6 +12,9 @@
 #include <unistd.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -30,12 +33,25 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+void prefer_max_smem_impl(const void* func) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({func, dev})) return;
+  if (getenv("DEFER_NO_CARVEOUT") == nullptr)
+    cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  done.insert({func, dev});
+}
+
 // ------------------------------------------------------------------------------------------ layout
-constexpr int MAX_DEPTH = 16;
-constexpr size_t CTRL_BYTES = 8192;
+constexpr int MAX_DEPTH = 32;
+constexpr size_t CTRL_BYTES = 16384;
 constexpr size_t FLAG_STRIDE = 128;  // one flag per 128-B line
-// ctrl block: [0,2048) ready[d] | [2048,4096) free[d] | [4096,..) local counters + status
-constexpr size_t OFF_READY = 0, OFF_FREE = 2048, OFF_CTR = 4096, OFF_STATUS = 8000;
+// ctrl block: [0,4096) ready[d] | [4096,8192) free[d] | [8192,..) local counters | status
+constexpr size_t OFF_READY = 0, OFF_FREE = 4096, OFF_CTR = 8192, OFF_STATUS = 12288;
 enum { CTR_WAIT_READY = 0, CTR_SIG_FREE = 1, CTR_WAIT_FREE = 2, CTR_SIG_READY = 3 };
 
 struct LinkToken {  // POD, <= DEFER_LINK_TOKEN_BYTES
@@ -65,6 +81,8 @@ struct Buf {
 struct OpRt {
   defer_op_desc d;
   int backend = 1;          // 1 SIMT, 2 tcgen05
+  bool persist = false;     // tcgen05 conv with many tiles: persistent-grid launch (overlapped epilogue)
+  int n_tiles64 = 0;
   UmmaConvPlan umma;        // valid when backend == 2
   std::string kname;
   double alg_bytes = 0, alg_flops = 0;
@@ -81,6 +99,7 @@ struct Lane {
   int* status_host = nullptr; // pinned copy of the sticky device status, refreshed every step (last stage)
   float* dense_partial = nullptr;
   std::vector<UmmaConvLaneArgs> umma;  // per op
+  std::vector<void*> persist_op;       // per op: device op descriptor for the persistent-grid launch
   bool timed = false;
 };
 
@@ -111,6 +130,13 @@ struct defer_stage_s {
   size_t flush_bytes = 0;
   size_t max_dense_partial = 0;
   cudaEvent_t job_t0 = nullptr, job_t1 = nullptr;
+  // megakernel groups: runs of consecutive tcgen05 convs executed by one cluster launch per lane
+  struct MegaGroup {
+    int first = 0, last = 0;
+    std::vector<void*> dev_ops;   // per lane: device array of op descriptors
+  };
+  std::vector<MegaGroup> groups;
+  std::vector<int> op_group;      // group index per op, -1 = launched on its own
 
   uint32_t* ctrl_u32(size_t off) { return reinterpret_cast<uint32_t*>(arena + off); }
   uint32_t* ready_flag(int d) { return ctrl_u32(OFF_READY + d * FLAG_STRIDE); }
@@ -143,7 +169,10 @@ static int launch_op(defer_stage_s* s, int lane_id, int oi, cudaStream_t st) {
   auto wptr = [&](int id) -> const float* { return id >= 0 ? (const float*)s->d_weights[id] : nullptr; };
   switch (d.kind) {
     case DEFER_OP_CONV: {
-      if (op.backend == 2) return launch_conv_umma(op.umma, L.umma[oi], st);
+      if (op.backend == 2) {
+        if (op.persist) return launch_conv_persistent(op.umma.nplanes, L.persist_op[oi], op.n_tiles64, st);
+        return launch_conv_umma(op.umma, L.umma[oi], st);
+      }
       ConvParams p;
       p.x = x; p.w = wptr(d.w_kernel); p.scale = wptr(d.w_scale); p.shift = wptr(d.w_shift);
       p.res = (d.flags & DEFER_FLAG_RESIDUAL) ? L.buf[d.in1] : nullptr;
@@ -195,11 +224,18 @@ static int enqueue_lane(defer_stage_s* s, int lane_id, cudaStream_t st) {
     DEFER_TRY(launch_wait_flag(s->ready_flag(lane_id), s->counter(CTR_WAIT_READY, lane_id), 0, s->status_ptr(),
                                s->timeout_ns, st));
   for (int oi = 0; oi < (int)s->ops.size(); ++oi) {
-    if (s->has_cons && oi == s->output_writer)
+    const int g = s->op_group.empty() ? -1 : s->op_group[oi];
+    if (g >= 0 && oi != s->groups[g].first) continue;          // executed by its group's launch
+    const int span_last = g >= 0 ? s->groups[g].last : oi;
+    if (s->has_cons && s->output_writer >= oi && s->output_writer <= span_last)
       DEFER_TRY(launch_wait_flag(s->free_flag(lane_id), s->counter(CTR_WAIT_FREE, lane_id), 1, s->status_ptr(),
                                  s->timeout_ns, st));
-    DEFER_TRY(launch_op(s, lane_id, oi, st));
-    if (s->has_prod && oi == s->last_input_reader) {
+    if (g >= 0) {
+      DEFER_TRY(launch_conv_mega(s->ops[oi].umma.nplanes, s->groups[g].dev_ops[lane_id], span_last - oi + 1, st));
+    } else {
+      DEFER_TRY(launch_op(s, lane_id, oi, st));
+    }
+    if (s->has_prod && s->last_input_reader >= oi && s->last_input_reader <= span_last) {
       uint32_t* remote = reinterpret_cast<uint32_t*>(s->prod_arena + OFF_FREE + lane_id * FLAG_STRIDE);
       DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_FREE, lane_id), st));
     }
@@ -583,6 +619,11 @@ int defer_stage_describe(defer_stage_t s, char* buf, size_t buf_len) {
     const OpRt& op = s->ops[i];
     const Buf& bi = s->bufs[op.d.in0];
     const Buf& bo = s->bufs[op.d.out];
+    if (!s->op_group.empty() && s->op_group[i] >= 0 && (int)i == s->groups[s->op_group[i]].first) {
+      snprintf(line, sizeof line, "  -- megakernel group: ops %d..%d in one cluster launch --\n", s->groups[s->op_group[i]].first,
+               s->groups[s->op_group[i]].last);
+      o += line;
+    }
     snprintf(line, sizeof line, "  [%2zu] %-22s in b%-3d(%d,%d,%d) res b%-3d -> b%-3d(%d,%d,%d) k=%dx%d s=%d flags=%u  %.3f MB %.3f GF\n", i,
              op.kname.c_str(), op.d.in0, bi.h, bi.w, bi.c, op.d.in1, op.d.out, bo.h, bo.w, bo.c, op.d.kh, op.d.kw, op.d.sh,
              op.d.flags, op.alg_bytes / 1e6, op.alg_flops / 1e9);
@@ -723,6 +764,26 @@ int defer_stage_finalize(defer_stage_t s) {
   DEFER_CHECK(s->cfg.is_first || s->has_prod, "finalize: stage is not first and has no producer link");
   DEFER_CHECK(s->cfg.is_last || s->has_cons, "finalize: stage is not last and has no consumer link");
   DEFER_TRY(set_device(s));
+  // megakernel groups: maximal runs of consecutive tcgen05 convs (DEFER_MEGA=0 disables)
+  s->op_group.assign(s->ops.size(), -1);
+  {
+    const char* e = getenv("DEFER_MEGA");
+    const bool mega_on = e && atoi(e) != 0;   // cluster-chain megakernel: opt-in (wins only when launch-bound)
+    int i = 0, n = (int)s->ops.size();
+    while (mega_on && i < n) {
+      if (s->ops[i].backend != 2) { ++i; continue; }
+      int j = i;
+      while (j + 1 < n && s->ops[j + 1].backend == 2) ++j;
+      if (j > i) {
+        defer_stage_s::MegaGroup g;
+        g.first = i;
+        g.last = j;
+        for (int k = i; k <= j; ++k) s->op_group[k] = (int)s->groups.size();
+        s->groups.push_back(g);
+      }
+      i = j + 1;
+    }
+  }
   // tcgen05 conv plans need final buffer addresses (TMA tensor maps embed them)
   for (int oi = 0; oi < (int)s->ops.size(); ++oi) {
     OpRt& op = s->ops[oi];
@@ -730,14 +791,55 @@ int defer_stage_finalize(defer_stage_t s) {
     const defer_op_desc& d = op.d;
     const Buf& bi = s->bufs[d.in0];
     const Buf& bo = s->bufs[d.out];
-    DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bi.h, bi.w, bi.c, bo.h, bo.w, bo.c, d.kh, d.kw, d.sh,
-                                d.sw, d.pad_t, d.pad_l, d.flags, (const float*)s->d_weights[d.w_kernel],
-                                d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
-                                d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr));
+    bool mega_plan = s->op_group[oi] >= 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bi.h, bi.w, bi.c, bo.h, bo.w, bo.c, d.kh, d.kw, d.sh,
+                                  d.sw, d.pad_t, d.pad_l, d.flags, (const float*)s->d_weights[d.w_kernel],
+                                  d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
+                                  d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan));
+      op.n_tiles64 = op.umma.tiles_n * op.umma.tiles_h * op.umma.tiles_w * (bo.c / 64);
+      const char* pe = getenv("DEFER_PERSIST_MIN_TILES");
+      const int min_tiles = pe ? atoi(pe) : 192;
+      op.persist = !mega_plan ? false : (s->op_group[oi] < 0);
+      if (attempt == 0 && !mega_plan && min_tiles > 0 && op.n_tiles64 >= min_tiles) {
+        umma_conv_release(op.umma);   // many tiles: re-plan for the persistent grid (BN = 64, no split-K)
+        mega_plan = true;
+        continue;
+      }
+      break;
+    }
+    if (op.persist) op.kname = "conv_mega_kernel(grid)";
     for (int l = 0; l < s->cfg.depth; ++l) {
       Lane& L = s->lanes[l];
       DEFER_TRY(umma_conv_bind(op.umma, &L.umma[oi], L.buf[d.in0],
                                (d.flags & DEFER_FLAG_RESIDUAL) ? L.buf[d.in1] : nullptr, L.buf[d.out]));
+    }
+  }
+  for (int oi = 0; oi < (int)s->ops.size(); ++oi) {
+    OpRt& op = s->ops[oi];
+    if (op.backend != 2 || !op.persist) continue;
+    const size_t ob = umma_mega_op_bytes();
+    std::vector<uint8_t> host(ob);
+    for (int l = 0; l < s->cfg.depth; ++l) {
+      Lane& L = s->lanes[l];
+      L.persist_op.resize(s->ops.size(), nullptr);
+      DEFER_TRY(umma_mega_fill(host.data(), op.umma, L.umma[oi]));
+      DEFER_CUDA(cudaMalloc(&L.persist_op[oi], ob));
+      s->workspace.push_back(L.persist_op[oi]);
+      DEFER_CUDA(cudaMemcpy(L.persist_op[oi], host.data(), ob, cudaMemcpyHostToDevice));
+    }
+  }
+  for (auto& g : s->groups) {
+    const int n = g.last - g.first + 1;
+    const size_t ob = umma_mega_op_bytes();
+    std::vector<uint8_t> host(ob * n);
+    g.dev_ops.assign(s->cfg.depth, nullptr);
+    for (int l = 0; l < s->cfg.depth; ++l) {
+      for (int k = 0; k < n; ++k)
+        DEFER_TRY(umma_mega_fill(host.data() + ob * k, s->ops[g.first + k].umma, s->lanes[l].umma[g.first + k]));
+      DEFER_CUDA(cudaMalloc(&g.dev_ops[l], ob * n));
+      s->workspace.push_back(g.dev_ops[l]);
+      DEFER_CUDA(cudaMemcpy(g.dev_ops[l], host.data(), ob * n, cudaMemcpyHostToDevice));
     }
   }
   DEFER_CUDA(cudaDeviceSynchronize());
@@ -874,7 +976,10 @@ int defer_stage_timer_stop(defer_stage_t s, float* ms) {
 int defer_stage_num_kernels(defer_stage_t s, int* per_step) {
   DEFER_CHECK(s && per_step, "num_kernels: null");
   int n = 0;
-  for (auto& op : s->ops) {
+  for (size_t i = 0; i < s->ops.size(); ++i) {
+    auto& op = s->ops[i];
+    const int g = s->op_group.empty() ? -1 : s->op_group[i];
+    if (g >= 0 && (int)i != s->groups[g].first) continue;   // one launch per megakernel group
     bool is_memcpy = op.d.kind == DEFER_OP_COPY && s->bufs[op.d.in0].elem == DEFER_BUF_F32 && s->bufs[op.d.out].elem == DEFER_BUF_F32;
     if (!is_memcpy) n += op.n_kernels;
   }

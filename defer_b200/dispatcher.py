@@ -31,7 +31,7 @@ from .node import DTYPE_TO_FMT, StageRunner, parse_device
 
 class DEFER:
     def __init__(self, computeNodes, *, dtype: str = "float32", depth: int = 4, batch: Optional[int] = None,
-                 conv_backend: int = 0, dist=None, wait_timeout_ms: int = 0) -> None:
+                 conv_backend: int = 0, dist=None, wait_timeout_ms: int = 0, max_inflight: int = 0) -> None:
         self.computeNodes = list(computeNodes)
         self.dispatchIP = "localhost"       # reference: socket.gethostbyname(...) (dispatcher.py:23); no sockets here
         self.chunk_size = 512 * 1000        # kept for interface parity (dispatcher.py:24)
@@ -41,6 +41,10 @@ class DEFER:
         self.conv_backend = conv_backend
         self.dist = dist                    # DistContext when launched one-process-per-GPU
         self.wait_timeout_ms = wait_timeout_ms
+        # microbatches between ingress and egress.  One process drives all stages => bounded by the lanes of
+        # the last stage (depth).  One process per GPU => every stage has its own `depth` lanes and the chain
+        # back-pressures itself through the device flags, so depth x stages may be in flight.
+        self.max_inflight = int(max_inflight)
         self.stages: List[StageRunner] = []
         self._stop = threading.Event()
         self._ready = threading.Event()
@@ -162,8 +166,10 @@ class DEFER:
         if self.batch is None:
             self.batch = 1
         models_to_dispatch = self._partition(model, partition_layers)
-        self._inflight = threading.Semaphore(self.depth)
-        self._hold = [None] * (2 * self.depth + 2)
+        if self.max_inflight <= 0:
+            self.max_inflight = self.depth * (self.dist.world if self.dist is not None else 1)
+        self._inflight = threading.Semaphore(self.max_inflight)
+        self._hold = [None] * (2 * self.max_inflight + 2)
         a = threading.Thread(target=self._result_server, args=(output_stream,), name="defer-result")
         a.start()
         try:
