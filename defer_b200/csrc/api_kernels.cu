@@ -1,6 +1,8 @@
 // api_kernels.cu - per-kernel C-ABI entry points (raw device pointers) for parity tests and ncu.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "conv_umma.cuh"
 
@@ -17,6 +19,59 @@ int defer_k_conv(int fmt, int backend, const void* x, int x_is_f32, const float*
   int ho = (h + pad_t + pad_b - kh) / sh + 1, wo = (w + pad_l + pad_r - kw) / sw + 1;
   DEFER_CHECK(ho >= 1 && wo >= 1, "k_conv: empty output");
   if (residual) flags |= DEFER_FLAG_RESIDUAL;
+  if (backend == 3) {
+    // persistent-grid tcgen05 kernel (the mode the stage runtime picks for ops with many tiles)
+    DEFER_CHECK(fmt != DEFER_FMT_F32 && !x_is_f32, "k_conv: tcgen05 backend needs BF16X2/BF16 activations");
+    DEFER_CHECK(umma_conv_supported(fmt, n, h, w, cin, ho, wo, cout, kh, kw, sh, sw, pad_t, pad_l),
+                "k_conv: shape not supported by the tcgen05 kernel");
+    UmmaConvPlan plan;
+    UmmaConvLaneArgs args;
+    void* dev_op = nullptr;
+    long long* trace = nullptr;
+    const char* trace_path = getenv("DEFER_UMMA_TRACE");
+    int rc = umma_conv_prepare(&plan, fmt, n, h, w, cin, ho, wo, cout, kh, kw, sh, sw, pad_t, pad_l, flags, w_hwio, scale, shift,
+                               /*mega=*/true);
+    if (rc == DEFER_OK) rc = umma_conv_bind(plan, &args, x, residual, y);
+    if (rc == DEFER_OK && trace_path) {
+      cudaMalloc((void**)&trace, 24 * 8 * sizeof(long long));
+      cudaMemset(trace, 0, 24 * 8 * sizeof(long long));
+      args.trace = trace;
+    }
+    std::vector<unsigned char> host(umma_mega_op_bytes());
+    if (rc == DEFER_OK) rc = umma_mega_fill(host.data(), plan, args);
+    if (rc == DEFER_OK && cudaMalloc(&dev_op, host.size()) != cudaSuccess) rc = DEFER_ERR_CUDA;
+    if (rc == DEFER_OK) cudaMemcpy(dev_op, host.data(), host.size(), cudaMemcpyHostToDevice);
+    const int n_tiles = plan.tiles_n * plan.tiles_h * plan.tiles_w * (cout / 64);
+    if (rc == DEFER_OK && trace) {   // warm-up so the traced launch sees warm descriptor / instruction caches
+      rc = launch_conv_persistent(plan.nplanes, dev_op, n_tiles, st);
+      cudaStreamSynchronize(st);
+      cudaMemset(trace, 0, 24 * 8 * sizeof(long long));
+    }
+    if (rc == DEFER_OK) rc = launch_conv_persistent(plan.nplanes, dev_op, n_tiles, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (trace) {
+      long long hb[24 * 8];
+      cudaMemcpy(hb, trace, sizeof hb, cudaMemcpyDeviceToHost);
+      FILE* f = fopen(trace_path, "a");
+      if (f) {
+        fprintf(f, "# persistent conv n=%d hw=%dx%d cin=%d cout=%d k=%d s=%d tiles=%d\n", n, h, w, cin, cout, kh, sh, n_tiles);
+        for (int i = 0; i < 24; ++i) {
+          if (!hb[i * 8]) continue;
+          fprintf(f, "%d", i);
+          for (int j = 0; j < 8; ++j) fprintf(f, " %lld", hb[i * 8 + j] ? hb[i * 8 + j] - hb[0] : -1);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      cudaFree(trace);
+    }
+    if (dev_op) cudaFree(dev_op);
+    umma_conv_unbind(&args);
+    umma_conv_release(plan);
+    if (rc != DEFER_OK) return rc;
+    DEFER_CUDA(e);
+    return DEFER_OK;
+  }
   if (backend == 2) {
     DEFER_CHECK(fmt != DEFER_FMT_F32 && !x_is_f32, "k_conv: tcgen05 backend needs BF16X2/BF16 activations");
     DEFER_CHECK(umma_conv_supported(fmt, n, h, w, cin, ho, wo, cout, kh, kw, sh, sw, pad_t, pad_l),

@@ -491,13 +491,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 struct alignas(128) MegaOp {
   CUtensorMap tmx[2];
   CUtensorMap tmw[2];
+  CUtensorMap tmy[2];       // output planes: 128-row x 64-channel boxes (TMA store, OOB rows clipped)
+  CUtensorMap tmr[2];       // residual planes, same geometry (TMA load into the staging tile)
   KParams p;
   int m_tiles, n_tiles;     // tiles of this op: m fastest
-  int pad_[2];
+  int direct;               // 1: per-thread st.global / ld.global epilogue (output in a peer GPU's slot)
+  int pad_[1];
 };
 
 constexpr int MEGA_BN = 64;
 constexpr int MEGA_ACC_BUFS = 2;
+constexpr int MEGA_EPI_WARPS = 8;
+constexpr int MEGA_THREADS = 64 + 32 * MEGA_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+__device__ __forceinline__ void mega_epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -513,25 +519,58 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// smem of the mega kernel: [stages x STAGE ring | 2 residual tiles | 2 output tiles | barriers]
+// (a tile = NPLANES x 128 rows x 128 B, SWIZZLE_128B rows)
 template <int NPLANES>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+struct MegaSmem {
+  using L = SmemLayout<NPLANES, MEGA_BN>;
+  static constexpr int STAGING = NPLANES * BM * 128;           // one output / residual tile, all planes
+  __host__ __device__ static constexpr int rbuf_off(int stages) { return stages * L::STAGE; }
+  __host__ __device__ static constexpr int obuf_off(int stages) { return stages * L::STAGE + 2 * STAGING; }
+  __host__ __device__ static constexpr int bar_off(int stages) { return stages * L::STAGE + 4 * STAGING; }
+  __host__ __device__ static constexpr int total(int stages) { return bar_off(stages) + 256 + 1024; }
+  __host__ __device__ static constexpr int max_stages() {
+    int s = (227 * 1024 - 4 * STAGING - 256 - 1024) / L::STAGE;
+    return s > 6 ? 6 : s;
+  }
+};
+
+template <int NPLANES>
+__global__ void __launch_bounds__(MEGA_THREADS, 1)
 conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_cluster, int* error_flag) {
   constexpr int BN = MEGA_BN;
   using L = SmemLayout<NPLANES, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
+  using MS = MegaSmem<NPLANES>;
   const int STAGES = stages;
-  const uint32_t bar_base = smem_base + L::bar_off(STAGES);
+  const uint32_t bar_base = smem_base + MS::bar_off(STAGES);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + MEGA_ACC_BUFS + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar_off(STAGES) + 8 * (2 * STAGES + 2 * MEGA_ACC_BUFS));
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };   // residual tile landed
+  auto rfree_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };   // residual tile consumed
+  auto ofree_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };   // output tile read by its TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MS::bar_off(STAGES) + 8 * (2 * STAGES + 10));
+  const uint32_t rbuf_base = smem_base + MS::rbuf_off(STAGES);
+  const uint32_t obuf_base = smem_base + MS::obuf_off(STAGES);
+  uint8_t* rbuf_ptr = smem + MS::rbuf_off(STAGES);
+  uint8_t* obuf_ptr = smem + MS::obuf_off(STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -547,7 +586,10 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
     }
     for (int b = 0; b < MEGA_ACC_BUFS; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);      // one arrival per epilogue warp
+      mbar_init(tempty_bar(b), MEGA_EPI_WARPS);      // one arrival per epilogue warp
+      mbar_init(rfull_bar(b), 1);
+      mbar_init(rfree_bar(b), MEGA_EPI_WARPS);
+      mbar_init(ofree_bar(b), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -563,10 +605,16 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // optional phase trace (debug): CTA 0 stamps globaltimer at role milestones of its first tiles
+  long long* trace = (n_ops > 0 && ops[0].p.trace && rank == 0) ? ops[0].p.trace : nullptr;
+  auto stamp = [&](uint32_t tile_seq, int slot) {
+    if (trace && tile_seq < 24) trace[tile_seq * 8 + slot] = (long long)gtimer();
+  };
   // running pipeline state of each role (every role walks the same (op, tile, k-block) sequence)
   int stage = 0;
   uint32_t phase = 0;
-  uint32_t it = 0;   // tiles processed by this CTA so far -> accumulator buffer / phase
+  uint32_t it = 0;       // tiles processed by this CTA so far -> accumulator / staging buffer and phase
+  uint32_t rit = 0;      // residual tiles so far -> residual buffer / phase (producer and epilogue warps)
 
   for (int oi = 0; oi < n_ops; ++oi) {
     const MegaOp& op = ops[oi];
@@ -585,7 +633,8 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
         prefetch_tmap(&op.tmw[0]);
         const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
         const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
-        for (int tile = rank; tile < n_tiles; tile += csize) {
+        const bool res_tma = p.res != nullptr && !op.direct;
+        for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
           const int mt = tile % op.m_tiles, nt = tile / op.m_tiles;
           int n0 = 0, h0 = 0, w0 = 0;
           if (p.flat) {
@@ -598,6 +647,18 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
             w0 = tw * p.tile_w;
           }
           const int c_base = nt * BN;
+          stamp(it, 0);   // producer starts issuing this tile
+          if (res_tma) {
+            // residual tile -> rbuf[rb] (its own full/free barrier pair: prefetched as early as the epilogue allows)
+            const uint32_t rb = rit & 1, ur = rit >> 1;
+            ++rit;
+            mbar_wait(rfree_bar(rb), (ur & 1) ^ 1, error_flag, 15);
+            mbar_expect_tx(rfull_bar(rb), NPLANES * a_rows * 128u);
+            const uint32_t dst = rbuf_base + rb * MS::STAGING;
+            tma_load_4d(dst, &op.tmr[0], rfull_bar(rb), c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+            if (NPLANES == 2)
+              tma_load_4d(dst + BM * 128, &op.tmr[1], rfull_bar(rb), c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+          }
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 11);
             const int tap = kb / p.cblocks;
@@ -633,6 +694,7 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
         for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
           const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
           mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 12);   // epilogue drained this accumulator
+          stamp(it, 1);   // MMA: accumulator available
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
           uint32_t accum = 0;
@@ -659,28 +721,42 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar(buf));
+          stamp(it, 2);   // MMA: all MMAs of the tile issued
         }
       }
       __syncwarp();
     } else {
       // =================================================================== epilogue (warps 2..5)
+      // 8 epilogue warps: warp w reads TMEM lane quarter (w & 3) (hardware rule) and the 32-column half
+      // ((w - 2) >> 2) of the 64-column accumulator - two warps per scheduler hide each other's latencies
       const int quarter = warp & 3;
       const int r = quarter * 32 + lane;
+      const int chalf = (warp - 2) >> 2;
       const bool relu = p.flags & DEFER_FLAG_RELU;
+      const bool direct = op.direct != 0;
+      const bool is_issuer = threadIdx.x == 64;     // elected thread: TMA stores + bulk-group bookkeeping
+      const float* scale_ptr = p.scale;             // hoisted: the op descriptor lives in global memory
+      const float* shift_ptr = p.shift;
+      float scv[32], sfv[32];                       // this warp's 32 channels of scale / shift
+      int cached_nt = -1;
       for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
         const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
         const int mt = tile % op.m_tiles, nt = tile / op.m_tiles;
         const int c_base = nt * BN;
+        int n0 = 0, h0 = 0, w0 = 0;
         bool valid;
         size_t pix;
         if (p.flat) {
-          int m = mt * BM + r;
+          w0 = mt * BM;
+          int m = w0 + r;
           valid = m < p.m_total;
           pix = (size_t)m;
         } else {
           int tw0 = mt % p.tiles_w;
           int t2 = mt / p.tiles_w;
-          int n0 = (t2 / p.tiles_h) * p.tile_n, h0 = (t2 % p.tiles_h) * p.tile_h, w0 = tw0 * p.tile_w;
+          n0 = (t2 / p.tiles_h) * p.tile_n;
+          h0 = (t2 % p.tiles_h) * p.tile_h;
+          w0 = tw0 * p.tile_w;
           int tw = r % p.tile_w;
           int t3 = r / p.tile_w;
           int th = t3 % p.tile_h;
@@ -689,40 +765,74 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
           valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
           pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
         }
+        // staging tiles: SWIZZLE_128B rows of 128 B (64 channels), one per plane
+        const bool use_rbuf = (p.res != nullptr) && !direct;
+        const uint32_t rb = rit & 1, ur = rit >> 1;
+        if (use_rbuf) ++rit;
+        uint8_t* ostg = obuf_ptr + buf * MS::STAGING + r * 128;
+        const uint8_t* rstg = rbuf_ptr + rb * MS::STAGING + r * 128;
+        const int sw = r & 7;
         const __nv_bfloat16* rbase =
-            (p.res && valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + c_base : nullptr;
+            (direct && p.res && valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + c_base : nullptr;
         uint4 rh[4], rl[4];
         auto load_res = [&](int c0) {
+          if (direct) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            rh[q] = *reinterpret_cast<const uint4*>(rbase + c0 + q * 8);
-            if (NPLANES == 2) rl[q] = *reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + q * 8);
+            for (int q = 0; q < 4; ++q) {
+              rh[q] = *reinterpret_cast<const uint4*>(rbase + c0 + q * 8);
+              if (NPLANES == 2) rl[q] = *reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + q * 8);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch = ((c0 >> 3) + q) ^ sw;
+              rh[q] = *reinterpret_cast<const uint4*>(rstg + ch * 16);
+              if (NPLANES == 2) rl[q] = *reinterpret_cast<const uint4*>(rstg + BM * 128 + ch * 16);
+            }
           }
         };
-        if (rbase) load_res(0);
+        const bool has_res = p.res != nullptr;
+        const int c0 = chalf * 32;
+        if (nt != cached_nt) {   // tiles run m-fastest: the channel block changes once per m_tiles tiles
+          cached_nt = nt;
+          const float4* sp = reinterpret_cast<const float4*>(scale_ptr + c_base + c0);
+          const float4* fp = reinterpret_cast<const float4*>(shift_ptr + c_base + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 a4 = scale_ptr ? __ldg(sp + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 b4 = shift_ptr ? __ldg(fp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            scv[4 * j] = a4.x; scv[4 * j + 1] = a4.y; scv[4 * j + 2] = a4.z; scv[4 * j + 3] = a4.w;
+            sfv[4 * j] = b4.x; sfv[4 * j + 1] = b4.y; sfv[4 * j + 2] = b4.z; sfv[4 * j + 3] = b4.w;
+          }
+        }
+        if (use_rbuf) mbar_wait(rfull_bar(rb), ur & 1, error_flag, 16);   // residual tile landed
+        if (has_res && (rbase || !direct)) load_res(c0);
+        if (use_rbuf) {                                                   // in registers: release the buffer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rfree_bar(rb));
+        }
+        if (is_issuer) stamp(it, 3);   // epilogue: residual in registers, waiting for the accumulator
         mbar_wait(tfull_bar(buf), aphase, error_flag, 14);
+        if (is_issuer) stamp(it, 4);   // epilogue: accumulator ready
         tc_fence_after();
         const uint32_t taddr_row = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        {
           uint32_t v[32];
           tmem_ld32(taddr_row + c0, v);
-          if (c0 + 32 >= BN) {
-            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+          {
+            // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
           }
-          if (!valid) continue;
+          if (!(direct && !valid)) {
           float acc[32];
           const int c = c_base + c0;
+          // per-channel scale / shift of this warp's 32 columns: 16 independent 16-B loads (L1-resident,
+          // pointers hoisted out of the op descriptor), issued before the accumulator wait
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float sc = p.scale ? __ldg(p.scale + c + j) : 1.f;
-            float sf = p.shift ? __ldg(p.shift + c + j) : 0.f;
-            acc[j] = fmaf(__uint_as_float(v[j]), sc, sf);
-          }
-          if (rbase) {
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(v[j]), scv[j], sfv[j]);
+          if (has_res && (rbase || !direct)) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rh[q]);
@@ -740,13 +850,17 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
                 }
               }
             }
-            if (c0 + 32 < BN) load_res(c0 + 32);
           }
           if (relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
           }
           __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.cout + c;
+          if (!direct) {
+            // obuf[buf] was last read by the TMA store of tile it-2 (issuer: wait_group.read 1 -> ofree)
+            const uint32_t u = it >> 1;
+            mbar_wait(ofree_bar(buf), buf == 0 ? ((u & 1) ^ 1) : (u & 1), error_flag, 17);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 h, l;
@@ -760,11 +874,41 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
                 hp[e] = pack_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
               }
             }
-            *reinterpret_cast<uint4*>(yp + q * 8) = h;
-            if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + q * 8) = l;
+            if (direct) {
+              *reinterpret_cast<uint4*>(yp + q * 8) = h;
+              if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + q * 8) = l;
+            } else {
+              const int ch = ((c0 >> 3) + q) ^ sw;
+              *reinterpret_cast<uint4*>(ostg + ch * 16) = h;
+              if (NPLANES == 2) *reinterpret_cast<uint4*>(ostg + BM * 128 + ch * 16) = l;
+            }
+          }
           }
         }
+        if (!direct) {
+          // staging tile complete -> one TMA store per plane (full 128-B rows, rows outside the tensor clipped)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (is_issuer) stamp(it, 5);   // epilogue: this thread's part of the tile is in staging
+          mega_epi_bar_sync();
+          if (is_issuer) stamp(it, 6);   // epilogue: all 8 warps done
+          if (is_issuer) {
+            const uint32_t src = obuf_base + buf * MS::STAGING;
+            tma_store_4d(&op.tmy[0], src, c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+            if (NPLANES == 2) tma_store_4d(&op.tmy[1], src + BM * 128, c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+            bulk_commit();
+          }
+        }
+        // one ofree arrival per tile (direct tiles too, so the parity bookkeeping stays uniform): the store of
+        // tile it-1 has finished reading obuf[buf ^ 1], which tile it+1 will fill
+        if (is_issuer) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(ofree_bar(buf ^ 1));
+          stamp(it, 7);   // epilogue: previous store has released its staging tile
+        }
+        __syncwarp();   // the issuer's warp reconverges before the next warp-collective tcgen05.ld
       }
+      // all output of this op must be globally visible before the next (dependent) op / kernel end
+      if (is_issuer) bulk_wait_all();
     }
   }
 
@@ -1003,6 +1147,37 @@ int umma_conv_bind(const UmmaConvPlan& P, UmmaConvLaneArgs* a, const void* x, co
   if (P.nplanes == 1) a->tmap_x[1] = a->tmap_x[0];
   a->res = res;
   a->y = y;
+  a->has_out_maps = false;
+  if (P.bn == MEGA_BN && P.splits == 1) {
+    // output / residual tiles as TMA boxes (persistent-grid and megakernel epilogues)
+    size_t yelems = (size_t)P.n * P.ho * P.wo * P.cout;
+    for (int pl = 0; pl < P.nplanes; ++pl) {
+      for (int which = 0; which < 2; ++which) {
+        const void* basep = which == 0 ? (const void*)y : res;
+        CUtensorMap* dst = which == 0 ? &a->tmap_y[pl] : &a->tmap_r[pl];
+        if (!basep) { memset(dst, 0, sizeof(CUtensorMap)); continue; }
+        uint8_t* base = (uint8_t*)basep + pl * yelems * 2;
+        uint32_t es[4] = {1, 1, 1, 1};
+        if (P.flat) {
+          uint64_t m = (uint64_t)P.n * P.ho * P.wo;
+          uint64_t dims[4] = {(uint64_t)P.cout, m, 1, 1};
+          uint64_t strides[3] = {(uint64_t)P.cout * 2, m * P.cout * 2, m * P.cout * 2};
+          uint32_t box[4] = {64, BM, 1, 1};
+          DEFER_TRY(encode_map(dst, base, 4, dims, strides, box, es));
+        } else {
+          uint64_t dims[4] = {(uint64_t)P.cout, (uint64_t)P.wo, (uint64_t)P.ho, (uint64_t)P.n};
+          uint64_t strides[3] = {(uint64_t)P.cout * 2, (uint64_t)P.wo * P.cout * 2, (uint64_t)P.ho * P.wo * P.cout * 2};
+          uint32_t box[4] = {64, (uint32_t)P.tile_w, (uint32_t)P.tile_h, (uint32_t)P.tile_n};
+          DEFER_TRY(encode_map(dst, base, 4, dims, strides, box, es));
+        }
+      }
+    }
+    if (P.nplanes == 1) {
+      a->tmap_y[1] = a->tmap_y[0];
+      a->tmap_r[1] = a->tmap_r[0];
+    }
+    a->has_out_maps = true;
+  }
   a->partial = nullptr;
   a->counters = nullptr;
   if (P.splits > 1) {
@@ -1064,6 +1239,11 @@ int umma_mega_fill(void* host_dst, const UmmaConvPlan& P, const UmmaConvLaneArgs
   op.tmx[1] = a.tmap_x[1];
   op.tmw[0] = P.tmap_w[0];
   op.tmw[1] = P.tmap_w[1];
+  op.tmy[0] = a.tmap_y[0];
+  op.tmy[1] = a.tmap_y[1];
+  op.tmr[0] = a.tmap_r[0];
+  op.tmr[1] = a.tmap_r[1];
+  op.direct = (a.direct_out || !a.has_out_maps || env_int("DEFER_EPILOGUE_DIRECT", 0)) ? 1 : 0;
   fill_kparams(P, a, &op.p);
   op.m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
   op.n_tiles = P.cout / MEGA_BN;
@@ -1087,11 +1267,12 @@ static int launch_mega_t(const void* dev_ops, int n_ops, int stages, cudaStream_
   static bool attr_set[64] = {false};
   int dev = 0;
   DEFER_CUDA(cudaGetDevice(&dev));
+  using MS = MegaSmem<NPLANES>;
   if (stages < 1) stages = 1;
-  if (stages > L::MAX_STAGES) stages = L::MAX_STAGES;
+  if (stages > MS::max_stages()) stages = MS::max_stages();
   if (dev < 64 && !attr_set[dev]) {
     DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::total(L::MAX_STAGES)));
+                                    MS::total(MS::max_stages())));
     DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     prefer_max_smem(conv_mega_kernel<NPLANES>);
     attr_set[dev] = true;
@@ -1100,8 +1281,8 @@ static int launch_mega_t(const void* dev_ops, int n_ops, int stages, cudaStream_
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(cluster, 1, 1);
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = L::total(stages);
+  cfg.blockDim = dim3(MEGA_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = MS::total(stages);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1124,25 +1305,27 @@ static int launch_persist_t(const void* dev_op, int n_tiles, cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   DEFER_CUDA(cudaGetDevice(&dev));
+  using MS = MegaSmem<NPLANES>;
   if (dev < 64 && !attr_set[dev]) {
     DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::total(L::MAX_STAGES)));
+                                    MS::total(MS::max_stages())));
     DEFER_CUDA(cudaFuncSetAttribute(conv_mega_kernel<NPLANES>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     prefer_max_smem(conv_mega_kernel<NPLANES>);
     attr_set[dev] = true;
   }
   static int sms = 0;
   if (!sms) DEFER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int stages = env_int("DEFER_PERSIST_STAGES", NPLANES == 2 ? 2 : 4);
-  if (stages > L::MAX_STAGES) stages = L::MAX_STAGES;
-  int per_sm = (227 * 1024) / L::total(stages);
+  int stages = env_int("DEFER_PERSIST_STAGES", MS::max_stages());
+  if (stages > MS::max_stages()) stages = MS::max_stages();
+  if (stages < 1) stages = 1;
+  int per_sm = (227 * 1024) / MS::total(stages);
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int grid = sms * per_sm;
   if (grid > n_tiles) grid = n_tiles;
   const MegaOp* ops = reinterpret_cast<const MegaOp*>(dev_op);
   int* err = nullptr;
-  conv_mega_kernel<NPLANES><<<grid, NUM_THREADS, L::total(stages), st>>>(ops, 1, stages, 0, err);
+  conv_mega_kernel<NPLANES><<<grid, MEGA_THREADS, MS::total(stages), st>>>(ops, 1, stages, 0, err);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -1152,7 +1335,7 @@ int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStr
 }
 
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st) {
-  int stages = env_int("DEFER_MEGA_STAGES", 2);   // 2 x 48 KB: two clusters' CTAs share an SM
+  int stages = env_int("DEFER_MEGA_STAGES", 3);
   return nplanes == 2 ? launch_mega_t<2>(dev_ops, n_ops, stages, st) : launch_mega_t<1>(dev_ops, n_ops, stages, st);
 }
 

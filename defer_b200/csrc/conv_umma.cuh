@@ -31,6 +31,10 @@ struct UmmaConvPlan {
 // Per-lane binding: tensor maps of the input activation planes + raw pointers for the epilogue.
 struct UmmaConvLaneArgs {
   CUtensorMap tmap_x[2];
+  CUtensorMap tmap_y[2];             // output tile boxes (TMA store epilogue), valid when has_out_maps
+  CUtensorMap tmap_r[2];             // residual tile boxes
+  bool has_out_maps = false;
+  bool direct_out = false;           // output lives in a peer GPU's slot: keep the per-thread st.global epilogue
   const void* res = nullptr;
   void* y = nullptr;
   float* partial = nullptr;          // split-K partial tiles (per lane: lanes run concurrently)

@@ -811,6 +811,8 @@ int defer_stage_finalize(defer_stage_t s) {
     if (op.persist) op.kname = "conv_mega_kernel(grid)";
     for (int l = 0; l < s->cfg.depth; ++l) {
       Lane& L = s->lanes[l];
+      // the stage output of a non-last stage is the next GPU's input slot: plain stores over NVLink
+      L.umma[oi].direct_out = (d.out == s->cfg.output_buf) && !s->cfg.is_last;
       DEFER_TRY(umma_conv_bind(op.umma, &L.umma[oi], L.buf[d.in0],
                                (d.flags & DEFER_FLAG_RESIDUAL) ? L.buf[d.in1] : nullptr, L.buf[d.out]));
     }

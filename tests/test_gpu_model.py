@@ -179,3 +179,35 @@ def test_vgg16_single_stage():
         r.close()
     ref = _oracle(m, x)
     assert _rel(y, ref) <= 1e-3
+
+
+def test_resnet152_8_stage_bf16_same_gpu():
+    """BASELINE config 5 shape on one GPU: ResNet152, 8 stages (cuts after blocks 5,11,...,41), bf16."""
+    m = applications.ResNet152()
+    x = applications.synthetic_input(1, seed=11)
+    cuts = applications.default_cuts(m, 8)
+    outs = _pipeline_on_one_gpu(m, cuts, x, "bfloat16", depth=2, n_items=3)
+    ref = _oracle(m, x)
+    for y in outs:
+        assert _rel(y, ref) <= 8e-2          # bf16 storage over 152 layers; fp32 path is checked at 1e-3 below
+        assert np.array_equal(y, outs[0])
+    outs32 = _pipeline_on_one_gpu(m, cuts, x, "float32", depth=2, n_items=2)
+    assert _rel(outs32[0], ref) <= 1e-3
+
+
+def test_vgg16_4_stage_both_cut_lists():
+    """BASELINE config 4: VGG16, 4 stages - pool cuts and the MAC-balanced conv cuts (post-ReLU hand-over)."""
+    m = applications.VGG16()
+    x = applications.synthetic_input(1, seed=12)
+    ref = _oracle(m, x)
+    for cuts in (["block1_pool", "block2_pool", "block3_pool"], ["block2_conv1", "block3_conv2", "block4_conv2"]):
+        outs = _pipeline_on_one_gpu(m, cuts, x, "float32", depth=2, n_items=2)
+        assert _rel(outs[0], ref) <= 1e-3, cuts
+
+
+def test_unfused_cut_points_on_gpu(resnet50, x224):
+    """Cuts that break the conv+BN+ReLU fusion exercise the standalone AFFINE / RELU / PAD kernels."""
+    cuts = ["conv1", "bn2a_branch2a" if False else "activation_9", "avg_pool"]
+    outs = _pipeline_on_one_gpu(resnet50, cuts, x224, "float32", depth=2, n_items=2)
+    ref = _oracle(resnet50, x224)
+    assert _rel(outs[0], ref) <= 1e-3
