@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--depth", type=int, default=0, help="in-flight microbatches (lanes); 0 = auto")
     ap.add_argument("--conv-backend", type=int, default=0)
+    ap.add_argument("--cuts", default="reference", choices=["reference", "balanced"],
+                    help="reference: test/test.py:18 list (8) / SURVEY 8d lists (2, 4); balanced: defer_b200.autocut "
+                         "on per-op times measured on rank 0's GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -237,8 +240,21 @@ def run_b200(args):
         node_thread = threading.Thread(target=node.run, name="defer-node", daemon=True)
         node_thread.start()
     t_defer = None
+    cut_info = None
     if rank == 0:
         cuts = applications.default_cuts(model, n_stages)
+        if args.cuts == "balanced" and n_stages > 1:
+            from defer_b200 import autocut
+            probe = StageRunner.from_model(model, device=local_rank, dtype=args.dtype, max_batch=B, depth=1)
+            try:
+                op_us = [max(1.0, probe.time_op(i, iters=10, flush_l2=False) - 2.0) for i in range(len(probe.plan.ops))]
+            finally:
+                probe.close()
+            cuts, stage_us = autocut.balanced_cuts(model, n_stages, op_costs=op_us)
+            cut_info = {"policy": "balanced (defer_b200.autocut, measured per-op us)", "cuts": cuts,
+                        "predicted_stage_us": [round(v, 1) for v in stage_us]}
+        else:
+            cut_info = {"policy": "reference list (test/test.py:18 for 8 stages; SURVEY 8d for 2/4)", "cuts": cuts}
         t_defer = threading.Thread(target=defer.run_defer, args=(model, cuts, in_q, out_q), daemon=True)
         t_defer.start()
         if not defer.wait_ready(600):
@@ -403,7 +419,7 @@ def run_b200(args):
         line = {"metric": "inferences_per_sec", "value": K * B / (ms * 1e-3), "unit": "inferences/s", "n_gpus": n_stages,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": {"float32": "bf16x3->f32", "float32_simt": "f32", "bfloat16": "bf16"}[args.dtype],
-                "data": "synthetic", "config": workload_config(args, depth), "clocks": clocks,
+                "data": "synthetic", "config": dict(workload_config(args, depth), cuts=cut_info), "clocks": clocks,
                 "gpu_launches": launches, "wall_ms_per_step": wall / K * 1e3,
                 "timing": "CUDA events per rank (first launch -> all lanes drained), max over ranks"}
         line.update(result)

@@ -1064,16 +1064,16 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
   const int m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
 
   // ---- N tile, split-K and ring depth.
-  // At batch 1 every conv is latency-bound, and with several microbatches in flight the GPU is bound by
-  // CTA-slot time (sum over launches of CTAs x duration / SMs).  So: fat tiles (BN = 128), split-K only
-  // when a launch would otherwise have a handful of CTAs, and a shallow smem ring for short K loops so
-  // that 2-4 CTAs share an SM and overlap each other's latencies.
-  P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= env_int("DEFER_UMMA_BN128_MIN_CTAS", 8)) ? 128 : 64;
+  // With several microbatches in flight the GPU is bound by L2->SM operand traffic and launch rate, not
+  // by the parallelism of one launch (measured: BN = 128 wherever C_out allows and split-K only below 4
+  // CTAs gave +16 % inferences/s over BN = 64 / 16-CTA targets).  The A tile is re-read once per N tile
+  // and the weights once per M tile, so fat N tiles cut traffic; split-K adds partial-tile traffic.
+  P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= env_int("DEFER_UMMA_BN128_MIN_CTAS", 1)) ? 128 : 64;
   int force_bn = env_int("DEFER_UMMA_BN", 0);
   if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) P.bn = force_bn;
   int ctas = m_tiles * (cout / P.bn);
   P.splits = 1;
-  int target = env_int("DEFER_UMMA_TARGET_CTAS", 16);
+  int target = env_int("DEFER_UMMA_TARGET_CTAS", 4);
   if (env_int("DEFER_UMMA_SPLITK", 1) && ctas < target && P.k_blocks >= 8) {
     int s = (target + ctas - 1) / ctas;
     int max_s = P.k_blocks / 4;          // keep >= 4 k-blocks (256 K elements) per split

@@ -6,6 +6,8 @@
 // kernels of the hop.  It also holds the exact-fp32 FFMA implicit-GEMM convolution that (a) serves
 // shapes the tcgen05 kernel does not take (C_in = 3 stem) and (b) is the in-library cross-check of
 // the tensor-core path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace defer {
@@ -176,6 +178,118 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   }
 }
 
+// =============================================================================================
+// RGB stem: 7x7 / stride 2, C_in = 3, C_out = 64 (+ bias/BN scale-shift + ReLU).  K = 147 is hostile to
+// TMA / UMMA (C_in = 3), so this is a direct fp32 convolution: one CTA = 8x8 output pixels x 64 channels,
+// the 21x21x3 input patch and the whole 7x7x3x64 filter bank live in shared memory, each thread owns
+// 4 consecutive pixels x 8 channels (32 fp32 accumulators) and per (kh, ci) reuses a 13-value input
+// window across the 7 kw taps (27 shared loads : 224 FFMA).
+// =============================================================================================
+constexpr int STEM_T = 8;                   // output tile edge
+constexpr int STEM_P = STEM_T * 2 + 5;      // input patch edge (21)
+
+template <int FOUT>
+__global__ void __launch_bounds__(128) stem7x7s2_kernel(const ConvParams p) {
+  __shared__ __align__(16) float s_in[STEM_P * STEM_P * 3];
+  __shared__ __align__(16) float s_w[147 * 64];
+  const int t = threadIdx.x;
+  const int tiles_w = (p.wo + STEM_T - 1) / STEM_T;
+  const int tiles_h = (p.ho + STEM_T - 1) / STEM_T;
+  int bid = blockIdx.x;
+  const int tw = bid % tiles_w;
+  bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int nb = bid / tiles_h;
+  const int oh0 = th * STEM_T, ow0 = tw * STEM_T;
+  const int ih0 = oh0 * 2 - p.pad_t, iw0 = ow0 * 2 - p.pad_l;
+
+  // filter bank [kh][kw][ci][co] is already the HWIO order of the shipped weights: straight copy
+  for (int i = t; i < 147 * 64 / 4; i += 128)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+  const float* xin = reinterpret_cast<const float*>(p.x) + (size_t)nb * p.h * p.w_in * 3;
+  for (int i = t; i < STEM_P * STEM_P * 3; i += 128) {
+    int ci = i % 3;
+    int pc = (i / 3) % STEM_P;
+    int pr = i / (3 * STEM_P);
+    int ih = ih0 + pr, iw = iw0 + pc;
+    float v = 0.f;
+    if (ih >= 0 && ih < p.h && iw >= 0 && iw < p.w_in) v = __ldg(xin + ((size_t)ih * p.w_in + iw) * 3 + ci);
+    s_in[i] = v;
+  }
+  __syncthreads();
+
+  const int cg = t >> 4;           // channel group: channels cg*8 .. cg*8+7
+  const int pg = t & 15;
+  const int prow = pg >> 1;        // output row in the tile
+  const int pc0 = (pg & 1) * 4;    // first of 4 consecutive output columns
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int kh = 0; kh < 7; ++kh) {
+    const float* rowp = s_in + ((prow * 2 + kh) * STEM_P + pc0 * 2) * 3;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      float win[13];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) win[j] = rowp[j * 3 + ci];
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((kh * 7 + kw) * 3 + ci) * 64 + cg * 8);
+        const float4 w0 = wp[0], w1 = wp[1];
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xv = win[2 * i + kw];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+        }
+      }
+    }
+  }
+
+  const size_t plane_out = (size_t)p.n * p.ho * p.wo * 64;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = p.scale ? __ldg(p.scale + cg * 8 + j) : 1.f;
+    sf[j] = p.shift ? __ldg(p.shift + cg * 8 + j) : 0.f;
+  }
+  const bool relu = p.flags & DEFER_FLAG_RELU;
+  const int oh = oh0 + prow;
+  if (oh >= p.ho) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ow = ow0 + pc0 + i;
+    if (ow >= p.wo) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(acc[i][j], sc[j], sf[j]);
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    const size_t o = (((size_t)nb * p.ho + oh) * p.wo + ow) * 64 + cg * 8;
+    act_store4<FOUT>(p.y, plane_out, o, make_float4(v[0], v[1], v[2], v[3]));
+    act_store4<FOUT>(p.y, plane_out, o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+static bool stem_eligible(const ConvParams& p, bool x_is_f32) {
+  return x_is_f32 && p.kh == 7 && p.kw == 7 && p.sh == 2 && p.sw == 2 && p.cin == 3 && p.cout == 64 && p.res == nullptr &&
+         getenv("DEFER_NO_STEM_KERNEL") == nullptr;
+}
+
+template <int FOUT>
+static int launch_stem_t(const ConvParams& p, cudaStream_t st) {
+  const int tiles = ((p.wo + STEM_T - 1) / STEM_T) * ((p.ho + STEM_T - 1) / STEM_T) * p.n;
+  prefer_max_smem(stem7x7s2_kernel<FOUT>);
+  stem7x7s2_kernel<FOUT><<<tiles, 128, 0, st>>>(p);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
 template <int FIN, int FOUT>
 static int launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
   int M = p.n * p.ho * p.wo;
@@ -192,6 +306,13 @@ static int launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
 }
 
 int launch_conv_simt(int fmt, bool x_is_f32, const ConvParams& p, cudaStream_t st) {
+  if (stem_eligible(p, x_is_f32)) {
+    switch (fmt) {
+      case FMT_F32: return launch_stem_t<FMT_F32>(p, st);
+      case FMT_BF16X2: return launch_stem_t<FMT_BF16X2>(p, st);
+      case FMT_BF16: return launch_stem_t<FMT_BF16>(p, st);
+    }
+  }
   switch (fmt) {
     case FMT_F32: return launch_conv_simt_t<FMT_F32, FMT_F32>(p, st);
     case FMT_BF16X2:
