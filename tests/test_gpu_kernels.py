@@ -210,3 +210,48 @@ def test_encode_decode_roundtrip(torch_cuda):
         assert np.array_equal(y, _quantise(x, fmt)), name
         if name == "bf16x2":
             assert np.max(np.abs(y - x) / np.abs(x)) < 2.0 ** -15
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+def test_conv_tcgen05_forced_split_k(torch_cuda, fmt_name, monkeypatch):
+    """Deterministic split-K (fixed-order reduction by the last CTA) on small-M, deep-K layers, with residual."""
+    torch, lib = torch_cuda
+    monkeypatch.setenv("DEFER_UMMA_FORCE_SPLITS", "3")
+    for i, shape in enumerate([(1, 7, 7, 512, 512, 3, 1, 1), (2, 14, 14, 1024, 256, 1, 1, 0), (1, 7, 7, 2048, 512, 1, 1, 0)]):
+        n, h, w, cin, cout, k, s, pad = shape
+        e1, y1, _ = _conv_case(torch, lib, fmt_name, 2, n, h, w, cin, cout, k, s, pad, relu=True, residual=(i != 1), seed=i)
+        e2, y2, _ = _conv_case(torch, lib, fmt_name, 2, n, h, w, cin, cout, k, s, pad, relu=True, residual=(i != 1), seed=i)
+        assert e1 <= TOL[fmt_name], (shape, e1)
+        assert np.array_equal(y1, y2)            # run-to-run deterministic
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+def test_conv_persistent_grid_kernel(torch_cuda, fmt_name):
+    """backend 3: the persistent-grid kernel (TMA-store / TMA-residual epilogue, double-buffered TMEM)."""
+    torch, lib = torch_cuda
+    for i, shape in enumerate([(8, 56, 56, 64, 256, 1, 1, 0), (4, 56, 56, 64, 64, 3, 1, 1), (8, 28, 28, 256, 512, 1, 2, 0),
+                               (3, 14, 14, 256, 256, 3, 1, 1)]):
+        n, h, w, cin, cout, k, s, pad = shape
+        err, _, _ = _conv_case(torch, lib, fmt_name, 3, n, h, w, cin, cout, k, s, pad, relu=(i % 2 == 0), residual=(i % 2 == 1), seed=i)
+        assert err <= TOL[fmt_name], (shape, err)
+
+
+def test_stem_kernel_f32_input(torch_cuda):
+    """The dedicated 7x7/2 RGB stem kernel (fp32 image in, stage format out) against the oracle."""
+    from oracle import keras_ref as R
+    torch, lib = torch_cuda
+    rng = np.random.default_rng(3)
+    for fmt_name in ("f32", "bf16x2", "bf16"):
+        fmt = FMTS[fmt_name]
+        x = rng.standard_normal((2, 224, 224, 3), dtype=np.float32)
+        wk = (rng.standard_normal((7, 7, 3, 64)) * 0.1).astype(np.float32)
+        sc = rng.uniform(0.5, 1.5, 64).astype(np.float32)
+        sf = rng.standard_normal(64).astype(np.float32)
+        ref = np.maximum(R.conv2d(np.pad(x.astype(np.float64), ((0, 0), (3, 3), (3, 3), (0, 0))), wk.astype(np.float64), None, (2, 2), "valid") * sc + sf, 0)
+        xd, wd = torch.from_numpy(x).cuda(), torch.from_numpy(wk).cuda()
+        sd, fd = torch.from_numpy(sc).cuda(), torch.from_numpy(sf).cuda()
+        yd = _alloc_act(torch, fmt, ref.size)
+        A.check(lib.defer_k_conv(fmt, 1, _ptr(xd), 1, _ptr(wd), _ptr(sd), _ptr(fd), None, _ptr(yd), 2, 224, 224, 3, 64, 7, 7, 2, 2,
+                                 3, 3, 3, 3, A.FLAG_RELU, None))
+        y = _decode(torch, lib, yd, fmt, ref.shape)
+        assert R.rel_err(y, ref) <= (5e-3 if fmt_name == "bf16" else 2e-5), fmt_name
