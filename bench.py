@@ -127,6 +127,10 @@ def cpu_reference_run(model, n_stages, x, steps, warmup, seconds=None):
     names = [model.input._keras_history[0].name] + cuts + [model.output._keras_history[0].name]
     parts = [dag_util.construct_model(model, names[i], names[i + 1], part_name=f"part{i+1}") for i in range(n_stages)]
     stages = [TorchCpuModel(p.to_json(), p.get_weights()) for p in parts]
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use the host's cores
+    want = int(os.environ.get("DEFER_CPU_THREADS", "0")) or max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
     cores = torch.get_num_threads()
     if n_stages == 1:
         for _ in range(warmup):
@@ -136,37 +140,55 @@ def cpu_reference_run(model, n_stages, x, steps, warmup, seconds=None):
         while True:
             stages[0].predict(x)
             n += 1
-            if (seconds is not None and time.perf_counter() - t0 >= seconds) or (seconds is None and n >= steps):
+            el = time.perf_counter() - t0
+            if (seconds is not None and el >= seconds) or (seconds is None and (n >= steps or el > 90.0)):
                 break
         dt = time.perf_counter() - t0
         return n / dt, dt / n * 1e3, cores, n
     torch.set_num_threads(max(1, cores // n_stages))   # N stage threads share the host cores
     qs = [queue.Queue(8) for _ in range(n_stages + 1)]
+    stop = threading.Event()
+
+    def put(q, item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def worker(i):
-        while True:
-            item = qs[i].get()
-            if item is None:
-                qs[i + 1].put(None)
+        while not stop.is_set():
+            try:
+                item = qs[i].get(timeout=0.1)
+            except queue.Empty:
+                continue
+            if not put(qs[i + 1], stages[i].predict(item)):
                 return
-            qs[i + 1].put(stages[i].predict(item))
 
-    ths = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n_stages)]
+    def feeder():
+        for _ in range(warmup + steps):
+            if not put(qs[0], x):
+                return
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(n_stages)] + [threading.Thread(target=feeder)]
     for t in ths:
         t.start()
-    total = warmup + steps
-    def feeder():
-        for _ in range(total):
-            qs[0].put(x)
-        qs[0].put(None)
-    threading.Thread(target=feeder, daemon=True).start()
     for _ in range(warmup):
         qs[-1].get()
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         qs[-1].get()
+        done += 1
+        if time.perf_counter() - t0 > 90.0:      # bounded sample: stop counting after 90 s
+            break
     dt = time.perf_counter() - t0
-    return steps / dt, dt / steps * 1e3, cores, steps
+    stop.set()
+    for t in ths:
+        t.join()
+    return done / dt, dt / done * 1e3, cores, done
 
 
 def run_reference(args):

@@ -22,6 +22,8 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "conv_umma.cuh"
 
@@ -55,7 +57,10 @@ struct KParams {
   unsigned int* counters;
   size_t plane_out;                               // n*ho*wo*cout (elements) - offset of the lo plane
   int* error_flag;
-  long long* trace;   // optional: 8 clock64 stamps per CTA (debug instrumentation)
+  long long* trace;     // optional: 8 clock64 stamps per CTA (debug instrumentation)
+  long long* timeline;  // optional (DEFER_TIMELINE): device-wide log, [0] = cursor, then 8 words per CTA
+  int timeline_cap;
+  int timeline_tag;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -171,8 +176,9 @@ struct SmemLayout {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int NPLANES, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+// EW = epilogue warps: 4 (192 threads, 2 CTAs/SM) or 8 (320 threads, 1 CTA/SM; warp pairs split the columns)
+template <int NPLANES, int BN, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
                  const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, const KParams p) {
   using L = SmemLayout<NPLANES, BN>;
@@ -188,11 +194,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   float* s_scale = reinterpret_cast<float*>(smem + L::scale_off(STAGES));
   float* s_shift = s_scale + BN;
   __shared__ int s_is_last;
+  __shared__ long long s_tl[4];   // timeline phases: setup done, first operands landed, accumulator ready, epilogue done
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   long long* trace = p.trace ? p.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   if (trace && threadIdx.x == 0) { trace[0] = clock64(); trace[7] = (long long)gtimer(); }
+  long long tl_t0 = 0;
+  if (p.timeline && threadIdx.x == 0) tl_t0 = (long long)gtimer();
 
   // ---- tile coordinates
   const int tile_id = blockIdx.x;
@@ -239,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) {
       int c = c_base + i;
       s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
       s_shift[i] = (p.shift && c < p.cout) ? p.shift[c] : 0.f;
@@ -250,6 +259,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (trace && threadIdx.x == 0) trace[1] = clock64();   // setup done
+  if (p.timeline && threadIdx.x == 0) s_tl[0] = (long long)gtimer();
 
   if (warp == 0) {
     // =================================================================== TMA producer
@@ -297,6 +307,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       for (int i = 0; i < num_kb; ++i) {
         mbar_wait(full_bar(stage), phase, p.error_flag, 2);
         if (trace && i == 0) trace[2] = clock64();           // first operands landed
+        if (p.timeline && i == 0) s_tl[1] = (long long)gtimer();
         tc_fence_after();
         const uint32_t a_addr = smem_base + stage * L::STAGE;
         const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
@@ -323,6 +334,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   } else {
     // =================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    constexpr int CH_PER_WARP = (BN / 32) * 4 / EW;               // 32-column chunks this warp handles
+    const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP * 32;     // EW == 4: 0
+    const int c_end = c_begin + CH_PER_WARP * 32;
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); };
     const int r = quarter * 32 + lane;           // accumulator row == tile-local pixel
     // row -> output pixel
     bool valid;
@@ -353,9 +368,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       }
     };
     const bool res_prefetched = rbase != nullptr && p.splits == 1;
-    if (res_prefetched) load_res(0);
+    if (res_prefetched) load_res(c_begin);
     mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
     if (trace && threadIdx.x == 64) trace[4] = clock64();   // accumulator visible to the epilogue
+    if (p.timeline && threadIdx.x == 64) s_tl[2] = (long long)gtimer();
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool relu = p.flags & DEFER_FLAG_RELU;
@@ -366,7 +382,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       const size_t tile_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
       float* mine = p.partial + ((tile_lin * p.splits + split) * BM + r) * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr_row + c0, v);
 #pragma unroll
@@ -376,14 +392,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
                              __uint_as_float(v[j + 3])));
       }
       __threadfence();
-      epi_bar_sync();
+      epi_sync();
       if (threadIdx.x == 64) {
         unsigned prev = atomicAdd(p.counters + tile_lin, 1u);
         int last = (prev == (unsigned)(p.splits - 1));
         if (last) p.counters[tile_lin] = 0;   // re-arm for the next launch
         s_is_last = last;
       }
-      epi_bar_sync();
+      epi_sync();
       do_final = s_is_last != 0;
       if (do_final) __threadfence();
     }
@@ -391,7 +407,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     if (do_final) {
       const size_t tile_lin = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float acc[32];
         if (p.splits > 1) {
 #pragma unroll
@@ -417,7 +433,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], s_scale[c0 + j], s_shift[c0 + j]);
         if (rbase) {
-          if (c0 == 0 && !res_prefetched) load_res(0);
+          if (c0 == c_begin && !res_prefetched) load_res(c_begin);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rh[q]);
@@ -435,7 +451,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
               }
             }
           }
-          if (c0 + 32 < BN) load_res(c0 + 32);   // next chunk's residual is in flight during this chunk's stores
+          if (c0 + 32 < c_end) load_res(c0 + 32);   // next chunk's residual is in flight during this chunk's stores
         }
         if (relu) {
 #pragma unroll
@@ -464,9 +480,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 
   // ---- teardown
   if (trace && threadIdx.x == 64) trace[5] = clock64();     // epilogue stores issued
+  if (p.timeline && threadIdx.x == 64) s_tl[3] = (long long)gtimer();
   tc_fence_before();
   __syncthreads();
   if (trace && threadIdx.x == 0) trace[6] = clock64();
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(p.timeline), 1ull);
+    if (slot < (unsigned long long)p.timeline_cap) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      long long* e = p.timeline + 8 + slot * 8;
+      e[0] = tl_t0;
+      e[1] = (long long)gtimer();
+      e[2] = (long long)smid;
+      e[3] = (long long)p.timeline_tag;
+      e[4] = s_tl[0];
+      e[5] = s_tl[1];
+      e[6] = s_tl[2];
+      e[7] = s_tl[3];
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     constexpr uint32_t ncols = BN < 32 ? 32 : BN;
@@ -977,23 +1010,23 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
   return DEFER_OK;
 }
 
-template <int NPLANES, int BN>
+template <int NPLANES, int BN, int EW>
 int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams& kp, cudaStream_t st) {
   using L = SmemLayout<NPLANES, BN>;
   static bool attr_set[64] = {false};
   int dev = 0;
   DEFER_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::total(L::MAX_STAGES)));
-    prefer_max_smem(conv_umma_kernel<NPLANES, BN>);
+    prefer_max_smem(conv_umma_kernel<NPLANES, BN, EW>);
     attr_set[dev] = true;
   }
   int stages = kp.stages < 1 ? 1 : (kp.stages > L::MAX_STAGES ? L::MAX_STAGES : kp.stages);
   KParams kq = kp;
   kq.stages = stages;
   dim3 grid(plan.tiles_n * plan.tiles_h * plan.tiles_w, plan.cout / BN, plan.splits);
-  conv_umma_kernel<NPLANES, BN><<<grid, NUM_THREADS, L::total(stages), st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
+  conv_umma_kernel<NPLANES, BN, EW><<<grid, 64 + 32 * EW, L::total(stages), st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
                                                                     plan.tmap_w[NPLANES - 1], kq);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
@@ -1014,6 +1047,7 @@ bool umma_conv_supported(int fmt, int n, int h, int w, int cin, int ho, int wo, 
   return true;
 }
 
+static void timeline_init();
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -1024,6 +1058,7 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
                       const float* shift_dev, bool mega) {
   UmmaConvPlan& P = *plan;
   P = UmmaConvPlan();
+  timeline_init();
   P.fmt = fmt;
   P.nplanes = fmt == FMT_BF16X2 ? 2 : 1;
   P.n = n; P.h = h; P.w = w; P.cin = cin; P.ho = ho; P.wo = wo; P.cout = cout;
@@ -1196,6 +1231,34 @@ void umma_conv_unbind(UmmaConvLaneArgs* a) {
   a->counters = nullptr;
 }
 
+// DEFER_TIMELINE=<path> (debug): every CTA of the per-op conv kernel logs {start, end, SM, op tag, 4 phase stamps}
+// with %globaltimer; written when a stage is destroyed; summarised by tools/timeline_stats.py.
+constexpr int TIMELINE_CAP = 1 << 19;
+static long long* g_timeline = nullptr;
+void umma_timeline_dump() {
+  const char* path = getenv("DEFER_TIMELINE");
+  if (!g_timeline || !path) return;
+  std::vector<long long> h(8 + (size_t)TIMELINE_CAP * 8);
+  if (cudaMemcpy(h.data(), g_timeline, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  long long n = h[0] < TIMELINE_CAP ? h[0] : TIMELINE_CAP;
+  FILE* f = fopen(path, "w");
+  if (!f) return;
+  for (long long i = 0; i < n; ++i) {
+    const long long* e = h.data() + 8 + i * 8;
+    fprintf(f, "%lld %lld %lld %lld %lld %lld %lld %lld\n", e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
+  }
+  fclose(f);
+}
+static void timeline_init() {   // called from umma_conv_prepare: never inside a stream capture
+  static bool tried = false;
+  if (tried) return;
+  tried = true;
+  if (!getenv("DEFER_TIMELINE")) return;
+  size_t bytes = (8 + (size_t)TIMELINE_CAP * 8) * sizeof(long long);
+  if (cudaMalloc((void**)&g_timeline, bytes) == cudaSuccess) cudaMemset(g_timeline, 0, bytes);
+  else g_timeline = nullptr;
+}
+
 static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KParams* out) {
   KParams& kp = *out;
   kp.n = P.n; kp.ho = P.ho; kp.wo = P.wo; kp.cout = P.cout;
@@ -1216,13 +1279,22 @@ static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KPara
   kp.plane_out = (size_t)P.n * P.ho * P.wo * P.cout;
   kp.error_flag = nullptr;
   kp.trace = a.trace;
+  kp.timeline = g_timeline;
+  kp.timeline_cap = g_timeline ? TIMELINE_CAP : 0;
+  kp.timeline_tag = (P.ho << 20) | (P.kh << 16) | (P.cout & 0xffff);
 }
 
 int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStream_t st) {
   KParams kp;
   fill_kparams(P, a, &kp);
-  if (P.nplanes == 2) return P.bn == 128 ? launch_t<2, 128>(P, a, kp, st) : launch_t<2, 64>(P, a, kp, st);
-  return P.bn == 128 ? launch_t<1, 128>(P, a, kp, st) : launch_t<1, 64>(P, a, kp, st);
+  // measured at batch 1 / 16 lanes: 4 warps + 2 CTAs/SM 11.4k inf/s, 8 warps + 1 CTA/SM 10.5k
+  static const int ew = env_int("DEFER_UMMA_EPI_WARPS", 4);
+  if (ew != 8) {
+    if (P.nplanes == 2) return P.bn == 128 ? launch_t<2, 128, 4>(P, a, kp, st) : launch_t<2, 64, 4>(P, a, kp, st);
+    return P.bn == 128 ? launch_t<1, 128, 4>(P, a, kp, st) : launch_t<1, 64, 4>(P, a, kp, st);
+  }
+  if (P.nplanes == 2) return P.bn == 128 ? launch_t<2, 128, 8>(P, a, kp, st) : launch_t<2, 64, 8>(P, a, kp, st);
+  return P.bn == 128 ? launch_t<1, 128, 8>(P, a, kp, st) : launch_t<1, 64, 8>(P, a, kp, st);
 }
 
 // ---- megakernel host side

@@ -51,6 +51,7 @@ int umma_conv_bind(const UmmaConvPlan& plan, UmmaConvLaneArgs* args, const void*
 void umma_conv_unbind(UmmaConvLaneArgs* args);
 int launch_conv_umma(const UmmaConvPlan& plan, const UmmaConvLaneArgs& args, cudaStream_t st);
 void umma_conv_release(UmmaConvPlan& plan);
+void umma_timeline_dump();   // DEFER_TIMELINE=<path>: write the per-CTA log collected so far
 
 // Stage megakernel: a run of consecutive convs in ONE cluster launch (conv_umma.cu, conv_mega_kernel).
 size_t umma_mega_op_bytes();

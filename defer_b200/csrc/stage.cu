@@ -579,6 +579,7 @@ int defer_stage_destroy(defer_stage_t s) {
   if (!s) return DEFER_OK;
   cudaSetDevice(s->cfg.device);
   cudaDeviceSynchronize();
+  umma_timeline_dump();
   for (auto& L : s->lanes) {
     if (L.exec) cudaGraphExecDestroy(L.exec);
     if (L.graph) cudaGraphDestroy(L.graph);
