@@ -29,6 +29,8 @@
 
 namespace defer {
 
+static int env_int(const char* name, int dflt);
+
 namespace {
 
 constexpr int BM = 128;          // UMMA M
@@ -61,6 +63,7 @@ struct KParams {
   long long* timeline;  // optional (DEFER_TIMELINE): device-wide log, [0] = cursor, then 8 words per CTA
   int timeline_cap;
   int timeline_tag;
+  int pdl;              // launched with programmatic stream serialization: wait for the producer grid before reading
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -258,6 +261,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl) {
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, scale/shift staging,
+    // descriptor prefetch) overlapped the tail of the previous kernel of this lane; its outputs are visible
+    // only after this wait.  Our own dependents may start their prologue right away.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   if (trace && threadIdx.x == 0) trace[1] = clock64();   // setup done
   if (p.timeline && threadIdx.x == 0) s_tl[0] = (long long)gtimer();
 
@@ -1026,6 +1036,24 @@ int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams&
   KParams kq = kp;
   kq.stages = stages;
   dim3 grid(plan.tiles_n * plan.tiles_h * plan.tiles_w, plan.cout / BN, plan.splits);
+  static const int pdl = env_int("DEFER_PDL", 0);
+  kq.pdl = pdl;
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
+    cfg.dynamicSmemBytes = L::total(stages);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DEFER_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<NPLANES, BN, EW>, a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
+                                  plan.tmap_w[NPLANES - 1], kq));
+    return DEFER_OK;
+  }
   conv_umma_kernel<NPLANES, BN, EW><<<grid, 64 + 32 * EW, L::total(stages), st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
                                                                     plan.tmap_w[NPLANES - 1], kq);
   DEFER_CUDA(cudaGetLastError());
@@ -1282,6 +1310,7 @@ static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KPara
   kp.timeline = g_timeline;
   kp.timeline_cap = g_timeline ? TIMELINE_CAP : 0;
   kp.timeline_tag = (P.ho << 20) | (P.kh << 16) | (P.cout & 0xffff);
+  kp.pdl = 0;
 }
 
 int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStream_t st) {

@@ -264,6 +264,8 @@ static void op_costs(defer_stage_s* s, OpRt& op) {
   switch (d.kind) {
     case DEFER_OP_CONV: {
       double wbytes = op.backend == 2 ? (double)fmt_bytes_per_elem(fmt) : 4.0;
+      // a 1x1 convolution with stride > 1 only ever touches the sampled pixels: count those, not the whole input
+      if (d.kh == 1 && d.kw == 1 && (d.sh > 1 || d.sw > 1)) in_b = nb * bo.h * bo.w * bi.c * ab(bi);
       op.alg_bytes = in_b + out_b + ((d.flags & DEFER_FLAG_RESIDUAL) ? out_b : 0.0) +
                      (double)d.kh * d.kw * bi.c * bo.c * wbytes + 2.0 * bo.c * 4.0;
       op.alg_flops = 2.0 * nb * bo.h * bo.w * bo.c * d.kh * d.kw * bi.c;
