@@ -138,8 +138,9 @@ int defer_k_dense(int fmt, const void* x, const float* w_io, const float* bias, 
                   int in_features, int units, uint32_t flags, void* stream) {
   DEFER_CHECK(x && w_io && y, "k_dense: null pointer");
   float* partial = nullptr;
-  size_t bytes = (size_t)dense_splits(n, in_features, units) * n * units * sizeof(float);
+  size_t bytes = dense_workspace_bytes(n, in_features, units);
   DEFER_CUDA(cudaMalloc((void**)&partial, bytes));
+  DEFER_CUDA(cudaMemsetAsync(partial, 0, bytes, (cudaStream_t)stream));
   int rc = launch_dense(fmt, x, w_io, false, bias, y, y_is_f32 != 0, partial, n, in_features, units, flags, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(partial);

@@ -113,12 +113,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // split v into (hi, lo) bf16 pairs for two values
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  __nv_bfloat162 h;
-  h.x = ha;
-  h.y = hb;
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = pack_bf16x2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+  hi = pack_bf16x2(a, b);   // one packed F2FP (round-to-nearest-even), not two scalar F2F on the slow conversion pipe
+  lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
 template <int FMT>
@@ -157,11 +153,16 @@ struct ConvParams {
 };
 
 int launch_conv_simt(int fmt, bool x_is_f32, const ConvParams& p, cudaStream_t st);
+// tensor-core stem: fp32 image -> [pixels, K_pad] patch matrix in the stage format (then a 1x1 tcgen05 conv)
+int launch_stem_im2col(int fmt, const float* x, void* out, int n, int h, int w, int cin, int kh, int kw, int sh, int sw,
+                       int pad_t, int pad_l, int ho, int wo, int K_pad, cudaStream_t st);
 int launch_maxpool(int fmt, const void* x, void* y, int n, int h, int w, int c, int ph, int pw, int sh, int sw,
                    int pad_t, int pad_l, int ho, int wo, cudaStream_t st);
 int launch_gap(int fmt, const void* x, void* y, int n, int h, int w, int c, cudaStream_t st);
-// dense: partial buffer must hold dense_splits(...) * n * units floats
+// dense: `partial` is a workspace of dense_workspace_bytes(...) bytes, zeroed once (arrival counters)
 int dense_splits(int n, int in_features, int units);
+// dense workspace: split partials + arrival counters of the fused kernel; must be zero-initialised once
+size_t dense_workspace_bytes(int n, int in_features, int units);
 int launch_dense(int fmt, const void* x, const void* w, bool w_is_bf16, const float* bias, void* y, bool y_is_f32,
                  float* partial, int n, int in_features, int units, uint32_t flags, cudaStream_t st);
 int launch_softmax(const float* x, float* y, int n, int c, cudaStream_t st);

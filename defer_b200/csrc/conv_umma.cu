@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -49,6 +50,9 @@ struct KParams {
   int cblocks;                                    // cin / 64
   int k_blocks;                                   // taps * cblocks
   int splits;
+  int cluster;                                    // 1: the `splits` CTAs of a tile form one thread-block cluster (DSMEM reduction)
+  int tma_epi;                                    // 1: staged epilogue - residual tile in by TMA, finished tile out by TMA store
+  int res_stage_bytes;                            // smem reserved for the residual tile (0 without residual / tma_epi)
   int stages;
   uint32_t flags;
   const float* scale;
@@ -158,6 +162,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// ---- TMA store (bulk async group) helpers
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- thread-block cluster / distributed shared memory
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
 // K-major A and B (bits 15, 16 = 0), N>>3 at bit 17, M>>4 at bit 24
 template <int BN>
@@ -178,23 +226,51 @@ struct SmemLayout {
   __host__ __device__ static constexpr int total(int stages) { return stages * STAGE + 256 + 2 * BN * 4 + 1024; }
 };
 
+// rows of one output / residual tile box (what a TMA load of it delivers, OOB rows included)
+__device__ __forceinline__ uint32_t a_rows_out(const KParams& p) {
+  return p.flat ? (uint32_t)BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
+}
+
+// accumulator row r of the tile at (n0, h0, w0) -> output pixel (linear NHW index) and whether it exists
+__device__ __forceinline__ void row_to_pixel(const KParams& p, int r, int n0, int h0, int w0, bool& valid, size_t& pix) {
+  if (p.flat) {
+    const int m = w0 + r;
+    valid = m < p.m_total;
+    pix = (size_t)m;
+  } else {
+    const int tw = r % p.tile_w;
+    const int t2 = r / p.tile_w;
+    const int th = t2 % p.tile_h;
+    const int tn = t2 / p.tile_h;
+    const int nn = n0 + tn, oh = h0 + th, ow = w0 + tw;
+    valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
+    pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 // EW = epilogue warps: 4 (192 threads, 2 CTAs/SM) or 8 (320 threads, 1 CTA/SM; warp pairs split the columns)
 template <int NPLANES, int BN, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
-                 const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1, const KParams p) {
+                 const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1,
+                 const __grid_constant__ CUtensorMap tmy0, const __grid_constant__ CUtensorMap tmy1,
+                 const __grid_constant__ CUtensorMap tmr0, const __grid_constant__ CUtensorMap tmr1, const KParams p) {
   using L = SmemLayout<NPLANES, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const int STAGES = p.stages;                      // ring depth chosen per launch (smem footprint <-> CTAs per SM)
-  const uint32_t bar_base = smem_base + L::bar_off(STAGES);
+  // layout: [operand ring: STAGES x STAGE | residual tile (staged epilogue with residual only) | barriers | scale, shift]
+  const int res_off = STAGES * L::STAGE;
+  const int ctl_off = res_off + p.res_stage_bytes;
+  const uint32_t bar_base = smem_base + ctl_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar_off(STAGES) + 8 * (2 * STAGES + 1));
-  float* s_scale = reinterpret_cast<float*>(smem + L::scale_off(STAGES));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ctl_off + 8 * (2 * STAGES + 1));
+  const uint32_t res_full_bar = bar_base + 8u * (2 * STAGES + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + ctl_off + 256);
   float* s_shift = s_scale + BN;
   __shared__ int s_is_last;
   __shared__ long long s_tl[4];   // timeline phases: setup done, first operands landed, accumulator ready, epilogue done
@@ -223,10 +299,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   const int c_base = blockIdx.y * BN;
   // split-K range
   const int split = blockIdx.z;
-  const int kb_per = (p.k_blocks + p.splits - 1) / p.splits;
-  const int kb_begin = split * kb_per;
-  const int kb_end = min(p.k_blocks, kb_begin + kb_per);
-  const int num_kb = kb_end - kb_begin;   // host guarantees >= 1
+  const int kb_begin = (split * p.k_blocks) / p.splits;          // balanced ranges; host guarantees k_blocks >= splits
+  const int kb_end = ((split + 1) * p.k_blocks) / p.splits;
+  const int num_kb = kb_end - kb_begin;
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
@@ -241,6 +316,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -279,6 +355,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
       const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
       (void)stage_bytes;
+      if (p.tma_epi && p.res) {
+        // staged epilogue: the residual tile (64-channel boxes, one per plane and 64-column half) does not depend on
+        // the MMAs - fetch it now, it lands while the K loop runs
+        prefetch_tmap(&tmr0);
+        constexpr int HALVES = BN / 64;
+        mbar_expect_tx(res_full_bar, (uint32_t)(NPLANES * HALVES) * a_rows_out(p) * 128u);
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          const uint32_t dst = smem_base + res_off + h * (BM * 128);
+          tma_load_4d(dst, &tmr0, res_full_bar, c_base + 64 * h, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+          if (NPLANES == 2)
+            tma_load_4d(dst + HALVES * (BM * 128), &tmr1, res_full_bar, c_base + 64 * h, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -349,22 +439,120 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     const int c_end = c_begin + CH_PER_WARP * 32;
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); };
     const int r = quarter * 32 + lane;           // accumulator row == tile-local pixel
-    // row -> output pixel
     bool valid;
     size_t pix;
-    if (p.flat) {
-      int m = w0 + r;
-      valid = m < p.m_total;
-      pix = (size_t)m;
+    row_to_pixel(p, r, n0, h0, w0, valid, pix);
+    if (p.cluster) {
+      // ---- cluster split-K, step 1: park this CTA's raw partial tile in its own shared memory.  The operand ring
+      // is free once tmem_full fires (all MMAs, hence all their smem reads, have completed).  Row stride BN + 4
+      // floats keeps the 16-B stores of a quarter-warp on distinct banks.
+      mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
+      if (trace && threadIdx.x == 64) trace[4] = clock64();
+      if (p.timeline && threadIdx.x == 64) s_tl[2] = (long long)gtimer();
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t red_row = smem_base + (uint32_t)r * (uint32_t)((BN + 4) * 4);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr_row + c0, v);   // warp-collective
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) sts4(red_row + (uint32_t)(c0 + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    } else if (p.tma_epi) {
+      // ---- staged epilogue.  Per-thread 16-B global accesses cost one LSU wavefront each (measured: ~8000 wavefronts
+      // per 128x128 tile = the whole epilogue).  Instead: finished values go into a SWIZZLE_128B staging tile (it
+      // aliases the operand ring, which is drained once tmem_full fires) and leave by ONE TMA store per plane and
+      // 64-column half; the residual tile was fetched by TMA during the K loop and is read with conflict-free LDS.
+      constexpr int HALVES = BN / 64;
+      constexpr int REGION = BM * 128;             // one (plane, half) tile: 128 rows x 128 B
+      const int sw = r & 7;
+      uint8_t* stg_row = smem + r * 128;
+      const uint8_t* res_row = smem + res_off + r * 128;
+      const bool has_res = p.res != nullptr;
+      const bool relu = p.flags & DEFER_FLAG_RELU;
+      if (has_res) mbar_wait(res_full_bar, 0, p.error_flag, 4);
+      mbar_wait(tmem_full_bar, 0, p.error_flag, 3);
+      if (trace && threadIdx.x == 64) trace[4] = clock64();
+      if (p.timeline && threadIdx.x == 64) s_tl[2] = (long long)gtimer();
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr_row + c0, v);   // warp-collective
+        if (!valid) continue;
+        const int half = c0 >> 6;
+        const int chb = (c0 & 63) >> 3;            // first 16-B chunk of this 32-column group inside its 128-B row
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+          const float4 sf = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+          acc[j] = fmaf(__uint_as_float(v[j]), sc.x, sf.x);
+          acc[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sf.y);
+          acc[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sf.z);
+          acc[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sf.w);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ch = (chb + q) ^ sw;
+            const uint4 rh4 = *reinterpret_cast<const uint4*>(res_row + half * REGION + ch * 16);
+            const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[q * 8 + 2 * e] += __uint_as_float(hw[e] << 16);
+              acc[q * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u);
+            }
+            if (NPLANES == 2) {
+              const uint4 rl4 = *reinterpret_cast<const uint4*>(res_row + (HALVES + half) * REGION + ch * 16);
+              const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[q * 8 + 2 * e] += __uint_as_float(lw[e] << 16);
+                acc[q * 8 + 2 * e + 1] += __uint_as_float(lw[e] & 0xffff0000u);
+              }
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 h, l;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (NPLANES == 2) {
+              split_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1], hp[e], lp[e]);
+            } else {
+              hp[e] = pack_bf16x2(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+            }
+          }
+          const int ch = (chb + q) ^ sw;
+          *reinterpret_cast<uint4*>(stg_row + half * REGION + ch * 16) = h;
+          if (NPLANES == 2) *reinterpret_cast<uint4*>(stg_row + (HALVES + half) * REGION + ch * 16) = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
+      epi_sync();
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          tma_store_4d(&tmy0, smem_base + h * REGION, c_base + 64 * h, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+          if (NPLANES == 2)
+            tma_store_4d(&tmy1, smem_base + (HALVES + h) * REGION, c_base + 64 * h, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+        }
+        bulk_commit();
+        bulk_wait_all();   // the tile is in global memory (and the staging tile is free) before this CTA retires
+      }
     } else {
-      int tw = r % p.tile_w;
-      int t2 = r / p.tile_w;
-      int th = t2 % p.tile_h;
-      int tn = t2 / p.tile_h;
-      int nn = n0 + tn, oh = h0 + th, ow = w0 + tw;
-      valid = (tn < p.tile_n) && nn < p.n && oh < p.ho && ow < p.wo;
-      pix = ((size_t)nn * p.ho + oh) * p.wo + ow;
-    }
     // the residual does not depend on the MMAs: fetch chunk 0 while the main loop is still running
     // (only on the direct path; with split-K the finishing CTA is not known yet)
     const __nv_bfloat16* rbase =
@@ -486,6 +674,67 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
         }
       }
     }
+    }   // !p.cluster
+  }
+
+  if (p.cluster) {
+    // ---- cluster split-K, step 2: the S CTAs of the cluster hold the S partial tiles of ONE output tile.  After a
+    // cluster barrier CTA j owns the tile rows {j, j + S, j + 2S, ...}: it sums the S partials of those rows in
+    // rank order (deterministic) straight out of its peers' shared memory (DSMEM), applies bias/BN, residual and
+    // ReLU and stores them - the K loop AND the epilogue are spread over S SMs, no global workspace.
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int FMT = NPLANES == 2 ? FMT_BF16X2 : FMT_BF16;
+      constexpr int NT = 32 * EW;                  // epilogue threads
+      constexpr int G = BN / 4;                    // float4 column groups per row
+      const int S = p.splits;                      // 2, 4 or 8
+      const int my_rank = (int)cluster_ctarank();
+      const int te = threadIdx.x - 64;
+      const int tpr = (NT * S) / BM;               // threads per row
+      const int q = te % tpr;
+      const int r = (te / tpr) * S + my_rank;
+      bool valid;
+      size_t pix;
+      row_to_pixel(p, r, n0, h0, w0, valid, pix);
+      if (valid) {
+        const bool relu = p.flags & DEFER_FLAG_RELU;
+        const uint32_t row_addr = smem_base + (uint32_t)r * (uint32_t)((BN + 4) * 4);
+        const size_t o = pix * p.cout + c_base;
+        auto reduce_groups = [&](int g, auto ngc) {
+          constexpr int NG = decltype(ngc)::value;
+          float4 v[NG][8];
+          float4 rs[NG];
+#pragma unroll
+          for (int u = 0; u < NG; ++u) {
+            const int col = (g + u * tpr) * 4;
+            if (p.res) rs[u] = act_load4<FMT>(p.res, p.plane_out, o + col);
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2)
+              if (s2 < S) v[u][s2] = dsmem_ld4(dsmem_map(row_addr + (uint32_t)col * 4u, (uint32_t)s2));
+          }
+#pragma unroll
+          for (int u = 0; u < NG; ++u) {
+            const int col = (g + u * tpr) * 4;
+            float4 a = v[u][0];
+#pragma unroll
+            for (int s2 = 1; s2 < 8; ++s2)
+              if (s2 < S) { a.x += v[u][s2].x; a.y += v[u][s2].y; a.z += v[u][s2].z; a.w += v[u][s2].w; }
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
+            const float4 sf = *reinterpret_cast<const float4*>(s_shift + col);
+            a.x = fmaf(a.x, sc.x, sf.x); a.y = fmaf(a.y, sc.y, sf.y); a.z = fmaf(a.z, sc.z, sf.z); a.w = fmaf(a.w, sc.w, sf.w);
+            if (p.res) { a.x += rs[u].x; a.y += rs[u].y; a.z += rs[u].z; a.w += rs[u].w; }
+            if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+            act_store4<FMT>(p.y, p.plane_out, o + col, a);
+          }
+        };
+        int g = q;
+        for (; g + tpr < G; g += 2 * tpr) reduce_groups(g, std::integral_constant<int, 2>());
+        if (g < G) reduce_groups(g, std::integral_constant<int, 1>());
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();   // no CTA may leave (and free its shared memory) while a peer still reads it
   }
 
   // ---- teardown
@@ -547,33 +796,6 @@ constexpr int MEGA_ACC_BUFS = 2;
 constexpr int MEGA_EPI_WARPS = 8;
 constexpr int MEGA_THREADS = 64 + 32 * MEGA_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 __device__ __forceinline__ void mega_epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // smem of the mega kernel: [stages x STAGE ring | 2 residual tiles | 2 output tiles | barriers]
 // (a tile = NPLANES x 128 rows x 128 B, SWIZZLE_128B rows)
@@ -1023,39 +1245,57 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
 template <int NPLANES, int BN, int EW>
 int launch_t(const UmmaConvPlan& plan, const UmmaConvLaneArgs& a, const KParams& kp, cudaStream_t st) {
   using L = SmemLayout<NPLANES, BN>;
+  constexpr int SMEM_MAX = 225 * 1024;   // opt-in limit is 227 KB per block INCLUDING static shared memory
   static bool attr_set[64] = {false};
   int dev = 0;
   DEFER_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::total(L::MAX_STAGES)));
+    DEFER_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NPLANES, BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     prefer_max_smem(conv_umma_kernel<NPLANES, BN, EW>);
     attr_set[dev] = true;
   }
   int stages = kp.stages < 1 ? 1 : (kp.stages > L::MAX_STAGES ? L::MAX_STAGES : kp.stages);
+  while (stages > 1 && L::total(stages) + kp.res_stage_bytes > SMEM_MAX) --stages;
+  const size_t smem = (size_t)L::total(stages) + kp.res_stage_bytes;
   KParams kq = kp;
   kq.stages = stages;
   dim3 grid(plan.tiles_n * plan.tiles_h * plan.tiles_w, plan.cout / BN, plan.splits);
   static const int pdl = env_int("DEFER_PDL", 0);
   kq.pdl = pdl;
-  if (pdl) {
+  // tensor maps of the output / residual tiles (staged epilogue); unused otherwise - pass valid dummies
+  const CUtensorMap& ty0 = kq.tma_epi ? a.tmap_y[0] : a.tmap_x[0];
+  const CUtensorMap& ty1 = kq.tma_epi ? a.tmap_y[NPLANES - 1] : a.tmap_x[0];
+  const CUtensorMap& tr0 = (kq.tma_epi && kq.res) ? a.tmap_r[0] : a.tmap_x[0];
+  const CUtensorMap& tr1 = (kq.tma_epi && kq.res) ? a.tmap_r[NPLANES - 1] : a.tmap_x[0];
+  if (pdl || kq.cluster) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = grid;
     cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
-    cfg.dynamicSmemBytes = L::total(stages);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (kq.cluster) {   // the `splits` CTAs of one output tile (grid.z) are one thread-block cluster
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 1;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = (unsigned)plan.splits;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     DEFER_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<NPLANES, BN, EW>, a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
-                                  plan.tmap_w[NPLANES - 1], kq));
+                                  plan.tmap_w[NPLANES - 1], ty0, ty1, tr0, tr1, kq));
     return DEFER_OK;
   }
-  conv_umma_kernel<NPLANES, BN, EW><<<grid, 64 + 32 * EW, L::total(stages), st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
-                                                                    plan.tmap_w[NPLANES - 1], kq);
+  conv_umma_kernel<NPLANES, BN, EW><<<grid, 64 + 32 * EW, smem, st>>>(a.tmap_x[0], a.tmap_x[NPLANES - 1], plan.tmap_w[0],
+                                                                    plan.tmap_w[NPLANES - 1], ty0, ty1, tr0, tr1, kq);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -1132,6 +1372,11 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
   // CTAs gave +16 % inferences/s over BN = 64 / 16-CTA targets).  The A tile is re-read once per N tile
   // and the weights once per M tile, so fat N tiles cut traffic; split-K adds partial-tile traffic.
   P.bn = (cout % 128 == 0 && (long long)m_tiles * (cout / 128) >= env_int("DEFER_UMMA_BN128_MIN_CTAS", 1)) ? 128 : 64;
+  // staged (TMA) epilogue: default.  With a residual the tile's residual copy needs its own shared memory (64 KB for a
+  // 128-wide fp32-parity tile); DEFER_UMMA_TE_RES_BN64=1 switches those ops to 64-wide tiles (two CTAs per SM, twice
+  // the CTAs) - measured equal within noise, so the wide tile stays the default.
+  P.tma_epi = env_int("DEFER_UMMA_TMA_EPI", 1) ? 1 : 0;
+  if (P.tma_epi && (flags & DEFER_FLAG_RESIDUAL) && env_int("DEFER_UMMA_TE_RES_BN64", 0)) P.bn = 64;
   int force_bn = env_int("DEFER_UMMA_BN", 0);
   if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) P.bn = force_bn;
   int ctas = m_tiles * (cout / P.bn);
@@ -1151,15 +1396,44 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
     int per = (P.k_blocks + force_split - 1) / force_split;
     P.splits = (P.k_blocks + per - 1) / per;
   }
+  // ---- cluster split-K (default): at batch 1 a launch has few tiles and each CTA's K loop is bound by what ONE SM
+  // can pull out of L2 (~0.7 us per 64 KB k-block measured), followed by a 128-column epilogue in one warp per
+  // scheduler.  A cluster of S CTAs per output tile cuts both by S; the partial tiles meet in distributed shared
+  // memory.  S = largest of {8, 4, 2} that leaves >= DEFER_UMMA_CSPLIT_KB k-blocks per CTA.
+  P.cluster = 0;
+  if (env_int("DEFER_UMMA_CLUSTER", 0) && force_split <= 0 && !mega) {
+    const int min_kb = env_int("DEFER_UMMA_CSPLIT_KB", 4);
+    int max_s = env_int("DEFER_UMMA_CSPLIT_MAX", 8);
+    if (max_s > 8) max_s = 8;
+    const int max_ctas = env_int("DEFER_UMMA_CSPLIT_MAX_CTAS", 256);
+    int s = 1;
+    for (int c = 2; c <= max_s; c *= 2)
+      if (P.k_blocks / c >= min_kb && (long long)ctas * c <= max_ctas) s = c;
+    int force_c = env_int("DEFER_UMMA_FORCE_CSPLIT", 0);
+    if ((force_c == 2 || force_c == 4 || force_c == 8) && P.k_blocks >= force_c) s = force_c;
+    P.splits = s;
+    P.cluster = s > 1 ? 1 : 0;
+  }
   if (mega) {   // megakernel tiles: one N-tile width, the whole K loop inside the tile
     P.bn = MEGA_BN;
     P.splits = 1;
+    P.cluster = 0;
   }
   {
     int kb_per = (P.k_blocks + P.splits - 1) / P.splits;
     int st = kb_per <= 2 ? kb_per : (kb_per <= 6 ? 2 : 4);
+    if (P.cluster) {
+      // short K loops: put every k-block in flight at once; the ring must also hold the fp32 partial tile
+      st = kb_per;
+      const int stage_bytes = P.nplanes * (BM + P.bn) * 128;
+      const int red_bytes = BM * (P.bn + 4) * 4;
+      const int need = (red_bytes + stage_bytes - 1) / stage_bytes;
+      int cap = env_int("DEFER_UMMA_CSPLIT_STAGES", 3);
+      if (st > cap) st = cap;
+      if (st < need) st = need;
+    }
     int force_st = env_int("DEFER_UMMA_STAGES", 0);
-    if (force_st > 0) st = force_st;
+    if (force_st > 0 && !P.cluster) st = force_st;
     P.stages = st;
   }
 
@@ -1211,8 +1485,8 @@ int umma_conv_bind(const UmmaConvPlan& P, UmmaConvLaneArgs* a, const void* x, co
   a->res = res;
   a->y = y;
   a->has_out_maps = false;
-  if (P.bn == MEGA_BN && P.splits == 1) {
-    // output / residual tiles as TMA boxes (persistent-grid and megakernel epilogues)
+  if (P.splits == 1) {
+    // output / residual tiles as 64-channel TMA boxes (staged epilogues: per-op, persistent-grid, megakernel)
     size_t yelems = (size_t)P.n * P.ho * P.wo * P.cout;
     for (int pl = 0; pl < P.nplanes; ++pl) {
       for (int which = 0; which < 2; ++which) {
@@ -1243,7 +1517,7 @@ int umma_conv_bind(const UmmaConvPlan& P, UmmaConvLaneArgs* a, const void* x, co
   }
   a->partial = nullptr;
   a->counters = nullptr;
-  if (P.splits > 1) {
+  if (P.splits > 1 && !P.cluster) {
     size_t tiles = (size_t)P.tiles_n * P.tiles_h * P.tiles_w * (P.cout / P.bn);
     DEFER_CUDA(cudaMalloc((void**)&a->partial, tiles * P.splits * BM * P.bn * sizeof(float)));
     DEFER_CUDA(cudaMalloc((void**)&a->counters, tiles * sizeof(unsigned int)));
@@ -1297,10 +1571,15 @@ static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KPara
   kp.cblocks = P.cin / 64;
   kp.k_blocks = P.k_blocks;
   kp.splits = P.splits;
+  kp.cluster = P.cluster;
   kp.stages = P.stages;
+  static const int epi_direct = env_int("DEFER_EPILOGUE_DIRECT", 0);
+  kp.tma_epi = (P.tma_epi && a.has_out_maps && !a.direct_out && P.splits == 1 && !P.cluster && !epi_direct) ? 1 : 0;
+  kp.res_stage_bytes = 0;
   kp.flags = P.flags;
   kp.scale = P.scale; kp.shift = P.shift;
   kp.res = (P.flags & DEFER_FLAG_RESIDUAL) ? a.res : nullptr;
+  if (kp.tma_epi && kp.res) kp.res_stage_bytes = P.nplanes * (P.bn / 64) * BM * 128;
   kp.y = a.y;
   kp.partial = a.partial;
   kp.counters = a.counters;

@@ -19,6 +19,8 @@ struct UmmaConvPlan {
   int bn = 64;             // N tile (cout per CTA)
   int k_blocks = 0;        // taps * cin / 64
   int splits = 1;          // split-K factor (grid.z)
+  int cluster = 0;         // 1: the splits of a tile are one thread-block cluster, reduced through DSMEM
+  int tma_epi = 1;         // staged epilogue (TMA residual load + TMA store) wherever one CTA owns a whole tile
   int stages = 4;          // smem ring depth (run-time: fewer stages -> more CTAs per SM)
   size_t smem_bytes = 0;
   void* w_dev = nullptr;   // transformed weights

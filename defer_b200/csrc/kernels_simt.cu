@@ -325,6 +325,72 @@ int launch_conv_simt(int fmt, bool x_is_f32, const ConvParams& p, cudaStream_t s
 }
 
 // =============================================================================================
+// Tensor-core stem, step 1: im2col of the fp32 RGB image into the stage's activation format.
+// Row m = output pixel, column k = (kh * KW + kw) * C_in + ci  (the HWIO order of the shipped filter, so the
+// filter bank IS the [K, C_out] GEMM operand), zero for taps in the padding and for k >= K up to K_pad (a
+// multiple of 64).  The result feeds the tcgen05 conv kernel as a 1x1 convolution over K_pad channels.
+// One thread = 8 consecutive k of one pixel: a 16-byte store per bf16 plane.
+// =============================================================================================
+template <int FMT>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, void* __restrict__ out, int n, int h,
+                                                          int w, int cin, int kh, int kw, int sh, int sw, int pad_t,
+                                                          int pad_l, int ho, int wo, int K, int K_pad) {
+  const int groups = K_pad >> 3;
+  const size_t total = (size_t)n * ho * wo * groups;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % groups);
+  const size_t pix = i / groups;
+  const int ow = (int)(pix % wo);
+  const size_t t2 = pix / wo;
+  const int oh = (int)(t2 % ho);
+  const int nb = (int)(t2 / ho);
+  const float* xin = x + (size_t)nb * h * w * cin;
+  float v[8];
+  int k = g * 8;
+  int tap = k / cin, ci = k - tap * cin;
+  int a = tap / kw, b = tap - a * kw;
+#pragma unroll
+  for (int j = 0; j < 8; ++j, ++k) {
+    float val = 0.f;
+    if (k < K) {
+      const int ih = oh * sh - pad_t + a, iw = ow * sw - pad_l + b;
+      if (ih >= 0 && ih < h && iw >= 0 && iw < w) val = __ldg(xin + ((size_t)ih * w + iw) * cin + ci);
+    }
+    v[j] = val;
+    if (++ci == cin) { ci = 0; if (++b == kw) { b = 0; ++a; } }
+  }
+  const size_t plane = (size_t)n * ho * wo * K_pad;
+  const size_t o = pix * K_pad + (size_t)g * 8;
+  act_store4<FMT>(out, plane, o, make_float4(v[0], v[1], v[2], v[3]));
+  act_store4<FMT>(out, plane, o + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+int launch_stem_im2col(int fmt, const float* x, void* out, int n, int h, int w, int cin, int kh, int kw, int sh, int sw,
+                       int pad_t, int pad_l, int ho, int wo, int K_pad, cudaStream_t st) {
+  const int K = kh * kw * cin;
+  if (K_pad % 64 != 0 || K_pad < K) {
+    set_error("stem im2col: bad K_pad %d for K %d", K_pad, K);
+    return DEFER_ERR_INVALID;
+  }
+  const size_t total = (size_t)n * ho * wo * (K_pad / 8);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  switch (fmt) {
+    case FMT_BF16X2:
+      prefer_max_smem(stem_im2col_kernel<FMT_BF16X2>);
+      stem_im2col_kernel<FMT_BF16X2><<<grid, 256, 0, st>>>(x, out, n, h, w, cin, kh, kw, sh, sw, pad_t, pad_l, ho, wo, K, K_pad);
+      break;
+    case FMT_BF16:
+      prefer_max_smem(stem_im2col_kernel<FMT_BF16>);
+      stem_im2col_kernel<FMT_BF16><<<grid, 256, 0, st>>>(x, out, n, h, w, cin, kh, kw, sh, sw, pad_t, pad_l, ho, wo, K, K_pad);
+      break;
+    default: set_error("stem im2col: format %d has no tensor-core path", fmt); return DEFER_ERR_INVALID;
+  }
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+// =============================================================================================
 // max-pool with fused ZeroPadding2D (taps outside the tensor read 0.0, as Keras' explicit pad does)
 // one thread per (pixel, 4 channels)
 // =============================================================================================
@@ -484,8 +550,190 @@ __global__ void __launch_bounds__(256) dense_reduce_kernel(const float* __restri
   act_store<FOUT>(y, total, i, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused dense (default when units % 4 == 0): ONE launch does the weight stream, the split reduction and the
+// bias / ReLU epilogue.  CTA = 8 warps x (32 lanes x 4 units): every warp takes every 8th row of the CTA's
+// K slice, so a thread has 8 independent 16-byte weight loads in flight per round trip; the 8 warps are
+// summed in warp order through shared memory, the per-split partial goes to global memory, and the LAST CTA
+// to arrive at a column block (arrival counter, self re-arming) adds the splits in split order - the result
+// does not depend on arrival order, no float atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int DF_THREADS = 256;
+constexpr int DF_WARPS = 8;
+constexpr int DF_COLS = 128;
+
+constexpr size_t DF_HEADER = 4096;   // arrival counters (one per 128-unit column block) live at the start of the workspace
+
+size_t dense_workspace_bytes(int n, int in_features, int units) {
+  return DF_HEADER + (size_t)dense_splits(n, in_features, units) * n * units * sizeof(float);
+}
+
+static int dense_fused_splits(int n, int F, int U) {
+  const int col_blocks = (U + DF_COLS - 1) / DF_COLS;
+  int want = (2 * 148 + col_blocks - 1) / col_blocks;
+  int max_split = F / 64;                   // >= 8 rows per warp
+  if (max_split < 1) max_split = 1;
+  int s = want < max_split ? want : max_split;
+  const int cap = dense_splits(n, F, U);    // the workspace is sized for dense_splits()
+  if (s > cap) s = cap;
+  int min_split = (F + 1023) / 1024;
+  if (s < min_split) s = min_split;
+  return s < 1 ? 1 : s;
+}
+
+template <int FMT, typename WT, int FOUT>
+__global__ void __launch_bounds__(DF_THREADS) dense_fused_kernel(const void* __restrict__ x, const WT* __restrict__ w,
+                                                                 const float* __restrict__ bias, void* __restrict__ y,
+                                                                 float* __restrict__ partial, unsigned int* __restrict__ counters,
+                                                                 int n, int F, int U, int rows_per_split, int splits,
+                                                                 uint32_t flags) {
+  extern __shared__ float dsm[];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbc = n < DENSE_MAXB ? n : DENSE_MAXB;
+  float* xs = dsm;                                       // [nbc][rows_per_split]
+  float* red = dsm + (((size_t)nbc * rows_per_split + 3) & ~(size_t)3);   // [DF_WARPS][nbc][DF_COLS], 16-byte aligned
+  const int ub = blockIdx.x * DF_COLS;
+  const int u0 = ub + lane * 4;
+  const int f0 = blockIdx.y * rows_per_split;
+  const int f1 = min(F, f0 + rows_per_split);
+  const int rows = f1 - f0;
+  const size_t plane = (size_t)n * F;
+  for (int b0 = 0; b0 < n; b0 += DENSE_MAXB) {
+    const int nb = min(DENSE_MAXB, n - b0);
+    __syncthreads();
+    for (int i = tid; i < nb * rows; i += DF_THREADS) {
+      int b = i / rows, f = i - b * rows;
+      xs[b * rows_per_split + f] = act_load<FMT>(x, plane, (size_t)(b0 + b) * F + f0 + f);
+    }
+    __syncthreads();
+    float acc[DENSE_MAXB][4];
+#pragma unroll
+    for (int b = 0; b < DENSE_MAXB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
+    if (u0 < U) {
+      const WT* wp = w + (size_t)f0 * U + u0;
+#pragma unroll 8
+      for (int f = warp; f < rows; f += DF_WARPS) {
+        float4 wv;
+        if constexpr (sizeof(WT) == 2) {
+          const uint2 r = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)f * U));
+          wv = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                           __uint_as_float(r.y & 0xffff0000u));
+        } else {
+          wv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wp) + (size_t)f * U));
+        }
+#pragma unroll
+        for (int b = 0; b < DENSE_MAXB; ++b)
+          if (b < nb) {
+            const float xv = xs[b * rows_per_split + f];
+            acc[b][0] = fmaf(xv, wv.x, acc[b][0]);
+            acc[b][1] = fmaf(xv, wv.y, acc[b][1]);
+            acc[b][2] = fmaf(xv, wv.z, acc[b][2]);
+            acc[b][3] = fmaf(xv, wv.w, acc[b][3]);
+          }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < DENSE_MAXB; ++b)
+      if (b < nb)
+        *reinterpret_cast<float4*>(red + ((size_t)warp * nbc + b) * DF_COLS + lane * 4) =
+            make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+    __syncthreads();
+    for (int i = tid; i < nb * DF_COLS; i += DF_THREADS) {
+      const int b = i / DF_COLS, c = i - b * DF_COLS;
+      if (ub + c < U) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < DF_WARPS; ++wq) sum += red[((size_t)wq * nbc + b) * DF_COLS + c];
+        __stcg(partial + ((size_t)blockIdx.y * n + b0 + b) * U + ub + c, sum);
+      }
+    }
+  }
+  // ---- arrival: the last CTA of this column block folds the splits (fixed order) and finishes the layer
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(counters + blockIdx.x, 1u);
+    const int last = prev == (unsigned)(splits - 1);
+    if (last) counters[blockIdx.x] = 0;   // re-arm for the next launch on this lane
+    s_last = last;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const size_t total = (size_t)n * U;
+  for (int i = tid; i < n * DF_COLS; i += DF_THREADS) {
+    const int b = i / DF_COLS, c = i - b * DF_COLS;
+    const int u = ub + c;
+    if (u >= U) continue;
+    float sum = 0.f;
+    for (int k = 0; k < splits; ++k) sum += __ldcg(partial + ((size_t)k * n + b) * U + u);
+    if (bias) sum += __ldg(bias + u);
+    if (flags & DEFER_FLAG_RELU) sum = fmaxf(sum, 0.f);
+    act_store<FOUT>(y, total, (size_t)b * U + u, sum);
+  }
+}
+
+template <int FMT, typename WT, int FOUT>
+static int launch_dense_fused_t(const void* x, const void* w, const float* bias, void* y, float* partial, unsigned int* counters,
+                                int n, int F, int U, uint32_t flags, cudaStream_t st) {
+  int splits = dense_fused_splits(n, F, U);
+  int rows = (F + splits - 1) / splits;
+  splits = (F + rows - 1) / rows;
+  const int nbc = n < DENSE_MAXB ? n : DENSE_MAXB;
+  const size_t smem = ((((size_t)nbc * rows + 3) & ~(size_t)3) + (size_t)DF_WARPS * nbc * DF_COLS) * sizeof(float);
+  if (smem > 96 * 1024) {
+    set_error("dense: smem %zu too large", smem);
+    return DEFER_ERR_INVALID;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(dense_fused_kernel<FMT, WT, FOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    prefer_max_smem(dense_fused_kernel<FMT, WT, FOUT>);
+    attr_set[dev] = true;
+  }
+  dim3 grid((U + DF_COLS - 1) / DF_COLS, splits);
+  dense_fused_kernel<FMT, WT, FOUT><<<grid, DF_THREADS, smem, st>>>(x, (const WT*)w, bias, y, partial, counters, n, F, U, rows,
+                                                                   splits, flags);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+template <int FMT, typename WT>
+static int launch_dense_fused_f(int fout, const void* x, const void* w, const float* bias, void* y, float* partial,
+                                unsigned int* counters, int n, int F, int U, uint32_t flags, cudaStream_t st) {
+  switch (fout) {
+    case FMT_F32: return launch_dense_fused_t<FMT, WT, FMT_F32>(x, w, bias, y, partial, counters, n, F, U, flags, st);
+    case FMT_BF16X2: return launch_dense_fused_t<FMT, WT, FMT_BF16X2>(x, w, bias, y, partial, counters, n, F, U, flags, st);
+    case FMT_BF16: return launch_dense_fused_t<FMT, WT, FMT_BF16>(x, w, bias, y, partial, counters, n, F, U, flags, st);
+  }
+  set_error("dense: bad output fmt %d", fout);
+  return DEFER_ERR_INVALID;
+}
+
 int launch_dense(int fmt, const void* x, const void* w, bool w_is_bf16, const float* bias, void* y, bool y_is_f32,
                  float* partial, int n, int F, int U, uint32_t flags, cudaStream_t st) {
+  static const bool fused_on = getenv("DEFER_DENSE_FUSED") == nullptr || atoi(getenv("DEFER_DENSE_FUSED")) != 0;
+  // workspace layout (dense_workspace_bytes): [arrival counters, 4 KB, zeroed once | split partials]
+  unsigned int* counters = reinterpret_cast<unsigned int*>(partial);
+  partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(partial) + DF_HEADER);
+  if (fused_on && U % 4 == 0 && (size_t)((U + DF_COLS - 1) / DF_COLS) * sizeof(unsigned int) <= DF_HEADER) {
+    const int fout = y_is_f32 ? FMT_F32 : fmt;
+    switch (fmt) {
+      case FMT_F32:
+        return w_is_bf16 ? launch_dense_fused_f<FMT_F32, __nv_bfloat16>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st)
+                         : launch_dense_fused_f<FMT_F32, float>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st);
+      case FMT_BF16X2:
+        return w_is_bf16 ? launch_dense_fused_f<FMT_BF16X2, __nv_bfloat16>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st)
+                         : launch_dense_fused_f<FMT_BF16X2, float>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st);
+      case FMT_BF16:
+        return w_is_bf16 ? launch_dense_fused_f<FMT_BF16, __nv_bfloat16>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st)
+                         : launch_dense_fused_f<FMT_BF16, float>(fout, x, w, bias, y, partial, counters, n, F, U, flags, st);
+      default: set_error("dense: bad fmt"); return DEFER_ERR_INVALID;
+    }
+  }
   int splits = dense_splits(n, F, U);
   int rows = (F + splits - 1) / splits;
   splits = (F + rows - 1) / rows;

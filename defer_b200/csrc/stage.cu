@@ -80,7 +80,9 @@ struct Buf {
 
 struct OpRt {
   defer_op_desc d;
-  int backend = 1;          // 1 SIMT, 2 tcgen05
+  int backend = 1;          // 1 SIMT, 2 tcgen05, 4 tensor-core stem (im2col of the fp32 image + tcgen05 1x1 conv)
+  int k_pad = 0;            // backend 4: padded patch length (multiple of 64)
+  void* w_pad = nullptr;    // backend 4: zero-padded [k_pad, cout] fp32 filter matrix
   bool persist = false;     // tcgen05 conv with many tiles: persistent-grid launch (overlapped epilogue)
   int n_tiles64 = 0;
   UmmaConvPlan umma;        // valid when backend == 2
@@ -100,6 +102,7 @@ struct Lane {
   float* dense_partial = nullptr;
   std::vector<UmmaConvLaneArgs> umma;  // per op
   std::vector<void*> persist_op;       // per op: device op descriptor for the persistent-grid launch
+  std::vector<void*> im2col;           // per op (backend 4): patch matrix scratch
   bool timed = false;
 };
 
@@ -169,7 +172,10 @@ static int launch_op(defer_stage_s* s, int lane_id, int oi, cudaStream_t st) {
   auto wptr = [&](int id) -> const float* { return id >= 0 ? (const float*)s->d_weights[id] : nullptr; };
   switch (d.kind) {
     case DEFER_OP_CONV: {
-      if (op.backend == 2) {
+      if (op.backend == 4)
+        DEFER_TRY(launch_stem_im2col(fmt, (const float*)x, L.im2col[oi], nb, bi.h, bi.w, bi.c, d.kh, d.kw, d.sh, d.sw, d.pad_t,
+                                     d.pad_l, bo.h, bo.w, op.k_pad, st));
+      if (op.backend == 2 || op.backend == 4) {
         if (op.persist) return launch_conv_persistent(op.umma.nplanes, L.persist_op[oi], op.n_tiles64, st);
         return launch_conv_umma(op.umma, L.umma[oi], st);
       }
@@ -263,7 +269,7 @@ static void op_costs(defer_stage_s* s, OpRt& op) {
   double in_b = nb * bi.h * bi.w * bi.c * ab(bi), out_b = nb * bo.h * bo.w * bo.c * ab(bo);
   switch (d.kind) {
     case DEFER_OP_CONV: {
-      double wbytes = op.backend == 2 ? (double)fmt_bytes_per_elem(fmt) : 4.0;
+      double wbytes = (op.backend == 2 || op.backend == 4) ? (double)fmt_bytes_per_elem(fmt) : 4.0;
       // a 1x1 convolution with stride > 1 only ever touches the sampled pixels: count those, not the whole input
       if (d.kh == 1 && d.kw == 1 && (d.sh > 1 || d.sw > 1)) in_b = nb * bo.h * bo.w * bi.c * ab(bi);
       op.alg_bytes = in_b + out_b + ((d.flags & DEFER_FLAG_RESIDUAL) ? out_b : 0.0) +
@@ -276,7 +282,7 @@ static void op_costs(defer_stage_s* s, OpRt& op) {
       double wb = s->d_weights_bf16[d.w_kernel] ? 2.0 : 4.0;
       op.alg_bytes = in_b + out_b + F * bo.c * wb + bo.c * 4.0;
       op.alg_flops = 2.0 * nb * F * bo.c;
-      op.n_kernels = 2;
+      op.n_kernels = (bo.c % 4 == 0 && (getenv("DEFER_DENSE_FUSED") == nullptr || atoi(getenv("DEFER_DENSE_FUSED")) != 0)) ? 1 : 2;   // fused: one launch
       break;
     }
     case DEFER_OP_ADD:
@@ -440,6 +446,19 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
         if (cfg->conv_backend == 1) can_umma = false;
         op.backend = can_umma ? 2 : 1;
         op.kname = can_umma ? "conv_umma_kernel" : "conv_simt_kernel";
+        // RGB stem (fp32 image in, few input channels): im2col to a K_pad-channel patch matrix, then the tcgen05 kernel
+        // as a 1x1 conv - the fp32 FFMA stem costs ~6 us of the WHOLE GPU per image, the tensor-core one < 1 us
+        // DEFER_TC_STEM: 0 off, 1 (default) strided stems (ResNet 7x7/2), 2 every eligible first conv (VGG's 3x3/1 too)
+        static const int tc_stem = getenv("DEFER_TC_STEM") ? atoi(getenv("DEFER_TC_STEM")) : 1;
+        const int K = d.kh * d.kw * bi.c;
+        if (tc_stem && cfg->conv_backend != 1 && cfg->fmt != DEFER_FMT_F32 && bi.elem == DEFER_BUF_F32 && bi.c < 64 && K <= 256 &&
+            bo.c % 64 == 0 && !(d.flags & DEFER_FLAG_RESIDUAL) && d.sh <= 2 && d.sw <= 2 &&
+            (tc_stem >= 2 || (d.sh == 2 && d.sw == 2))) {
+          op.backend = 4;
+          op.k_pad = (K + 63) / 64 * 64;
+          op.kname = "stem_im2col+conv_umma_kernel";
+          op.n_kernels = 2;
+        }
         break;
       }
       case DEFER_OP_MAXPOOL:
@@ -451,13 +470,13 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
         break;
       case DEFER_OP_GAP: op.kname = "gap_kernel"; break;
       case DEFER_OP_DENSE: {
-        op.kname = "dense_partial_kernel";
+        op.kname = (bo.c % 4 == 0 && (getenv("DEFER_DENSE_FUSED") == nullptr || atoi(getenv("DEFER_DENSE_FUSED")) != 0)) ? "dense_fused_kernel" : "dense_partial_kernel";
         size_t F = (size_t)bi.h * bi.w * bi.c;
         if (d.w_kernel < 0 || s->weight_bytes[d.w_kernel] != F * bo.c * 4 || bi.elem != DEFER_BUF_ACT) {
           set_error("op %d (dense): kernel size mismatch (F=%zu U=%d)", i, F, bo.c);
           return fail(DEFER_ERR_INVALID);
         }
-        size_t need = (size_t)dense_splits(cfg->batch, (int)F, bo.c) * cfg->batch * bo.c * sizeof(float);
+        size_t need = dense_workspace_bytes(cfg->batch, (int)F, bo.c);
         if (need > s->max_dense_partial) s->max_dense_partial = need;
         if (cfg->fmt == DEFER_FMT_BF16 && !s->d_weights_bf16[d.w_kernel]) {
           void* wb = nullptr;
@@ -558,6 +577,10 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
         return fail(DEFER_ERR_CUDA);
       }
       s->workspace.push_back(L.dense_partial);
+      if (cudaMemset(L.dense_partial, 0, s->max_dense_partial) != cudaSuccess) {   // arrival counters of the fused dense kernel
+        set_error("cudaMemset dense workspace failed");
+        return fail(DEFER_ERR_CUDA);
+      }
     }
     if (cfg->is_last) {
       if (cudaMallocHost((void**)&L.out_host, s->bufs[cfg->output_buf].elems * 4) != cudaSuccess ||
@@ -595,7 +618,7 @@ int defer_stage_destroy(defer_stage_t s) {
     if (L.status_host) cudaFreeHost(L.status_host);
   }
   for (auto& op : s->ops)
-    if (op.backend == 2) umma_conv_release(op.umma);
+    if (op.backend == 2 || op.backend == 4) umma_conv_release(op.umma);
   for (void* p : s->workspace) cudaFree(p);
   for (void* p : s->d_weights) if (p) cudaFree(p);
   for (void* p : s->d_weights_bf16) if (p) cudaFree(p);
@@ -631,6 +654,13 @@ int defer_stage_describe(defer_stage_t s, char* buf, size_t buf_len) {
              op.kname.c_str(), op.d.in0, bi.h, bi.w, bi.c, op.d.in1, op.d.out, bo.h, bo.w, bo.c, op.d.kh, op.d.kw, op.d.sh,
              op.d.flags, op.alg_bytes / 1e6, op.alg_flops / 1e9);
     o += line;
+    if ((op.backend == 2 || op.backend == 4) && op.umma.ready) {
+      const UmmaConvPlan& u = op.umma;
+      snprintf(line, sizeof line, "       tcgen05 tiles: m=%d x n=%d (BN %d) x k-splits %d%s, %d k-blocks, ring %d -> %d CTAs\n",
+               u.tiles_n * u.tiles_h * u.tiles_w, u.cout / u.bn, u.bn, u.splits, u.cluster ? " (cluster, DSMEM reduce)" : "",
+               u.k_blocks, u.stages, u.tiles_n * u.tiles_h * u.tiles_w * (u.cout / u.bn) * u.splits);
+      o += line;
+    }
   }
   strncpy(buf, o.c_str(), buf_len - 1);
   buf[buf_len - 1] = 0;
@@ -790,12 +820,27 @@ int defer_stage_finalize(defer_stage_t s) {
   // tcgen05 conv plans need final buffer addresses (TMA tensor maps embed them)
   for (int oi = 0; oi < (int)s->ops.size(); ++oi) {
     OpRt& op = s->ops[oi];
-    if (op.backend != 2) continue;
+    if (op.backend != 2 && op.backend != 4) continue;
     const defer_op_desc& d = op.d;
     const Buf& bi = s->bufs[d.in0];
     const Buf& bo = s->bufs[d.out];
     bool mega_plan = s->op_group[oi] >= 0;
+    const bool stem = op.backend == 4;
+    if (stem && !op.w_pad) {
+      // [K, cout] filter bank (HWIO flattened) zero-padded to [k_pad, cout]
+      const size_t kc = (size_t)d.kh * d.kw * bi.c * bo.c;
+      DEFER_CUDA(cudaMalloc(&op.w_pad, (size_t)op.k_pad * bo.c * sizeof(float)));
+      s->workspace.push_back(op.w_pad);
+      DEFER_CUDA(cudaMemset(op.w_pad, 0, (size_t)op.k_pad * bo.c * sizeof(float)));
+      DEFER_CUDA(cudaMemcpy(op.w_pad, s->d_weights[d.w_kernel], kc * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
+      if (stem)   // 1x1 conv over the patch matrix: "image" = output grid, channels = k_pad
+        DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bo.h, bo.w, op.k_pad, bo.h, bo.w, bo.c, 1, 1, 1, 1, 0, 0,
+                                    d.flags, (const float*)op.w_pad,
+                                    d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
+                                    d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan));
+      else
       DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bi.h, bi.w, bi.c, bo.h, bo.w, bo.c, d.kh, d.kw, d.sh,
                                   d.sw, d.pad_t, d.pad_l, d.flags, (const float*)s->d_weights[d.w_kernel],
                                   d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
@@ -816,13 +861,23 @@ int defer_stage_finalize(defer_stage_t s) {
       Lane& L = s->lanes[l];
       // the stage output of a non-last stage is the next GPU's input slot: plain stores over NVLink
       L.umma[oi].direct_out = (d.out == s->cfg.output_buf) && !s->cfg.is_last;
-      DEFER_TRY(umma_conv_bind(op.umma, &L.umma[oi], L.buf[d.in0],
+      const void* conv_in = L.buf[d.in0];
+      if (stem) {
+        if (L.im2col.size() < s->ops.size()) L.im2col.resize(s->ops.size(), nullptr);
+        if (!L.im2col[oi]) {
+          const size_t bytes = (size_t)s->cfg.batch * bo.h * bo.w * op.k_pad * fmt_bytes_per_elem(s->cfg.fmt);
+          DEFER_CUDA(cudaMalloc(&L.im2col[oi], bytes));
+          s->workspace.push_back(L.im2col[oi]);
+        }
+        conv_in = L.im2col[oi];
+      }
+      DEFER_TRY(umma_conv_bind(op.umma, &L.umma[oi], conv_in,
                                (d.flags & DEFER_FLAG_RESIDUAL) ? L.buf[d.in1] : nullptr, L.buf[d.out]));
     }
   }
   for (int oi = 0; oi < (int)s->ops.size(); ++oi) {
     OpRt& op = s->ops[oi];
-    if (op.backend != 2 || !op.persist) continue;
+    if ((op.backend != 2 && op.backend != 4) || !op.persist) continue;
     const size_t ob = umma_mega_op_bytes();
     std::vector<uint8_t> host(ob);
     for (int l = 0; l < s->cfg.depth; ++l) {

@@ -182,6 +182,33 @@ def test_maxpool_gap_dense_softmax(torch_cuda, fmt_name):
 
 
 @pytest.mark.parametrize("fmt_name", ["f32", "bf16x2", "bf16"])
+def test_dense_fused_single_launch(torch_cuda, fmt_name):
+    """Fused dense (weight stream + split reduction by the last-arriving CTA + bias/ReLU in one launch): batch chunks
+    beyond 8 rows, ReLU, ragged K splits, the units % 4 != 0 fallback, and run-to-run determinism."""
+    from oracle import keras_ref as R
+    torch, lib = torch_cuda
+    fmt = FMTS[fmt_name]
+    rng = np.random.default_rng(11)
+    for n, F, U, relu in [(1, 2048, 1000, False), (3, 4096, 512, True), (9, 520, 1000, False), (2, 1000, 1002, True),
+                          (2, 4096, 1000, False), (1, 4096, 4096, True)]:
+        x = rng.standard_normal((n, F), dtype=np.float32)
+        wk = (rng.standard_normal((F, U)) * 0.03).astype(np.float32)
+        b = (rng.standard_normal(U) * 0.1).astype(np.float32)
+        ref = _quantise(x, fmt).astype(np.float64) @ wk.astype(np.float64) + b
+        if relu:
+            ref = np.maximum(ref, 0)
+        xd = _encode(torch, lib, x, fmt)
+        wd, bd = torch.from_numpy(wk).cuda(), torch.from_numpy(b).cuda()
+        outs = []
+        for _ in range(2):
+            yd = torch.empty(n * U, dtype=torch.float32, device="cuda")
+            A.check(lib.defer_k_dense(fmt, _ptr(xd), _ptr(wd), _ptr(bd), _ptr(yd), 1, n, F, U, A.FLAG_RELU if relu else 0, None))
+            outs.append(yd.cpu().numpy().reshape(n, U))
+        assert R.rel_err(outs[0], ref) <= 1e-5, (n, F, U, R.rel_err(outs[0], ref))
+        assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("fmt_name", ["f32", "bf16x2", "bf16"])
 def test_eltwise(torch_cuda, fmt_name):
     torch, lib = torch_cuda
     fmt = FMTS[fmt_name]
@@ -223,6 +250,62 @@ def test_conv_tcgen05_forced_split_k(torch_cuda, fmt_name, monkeypatch):
         e2, y2, _ = _conv_case(torch, lib, fmt_name, 2, n, h, w, cin, cout, k, s, pad, relu=True, residual=(i != 1), seed=i)
         assert e1 <= TOL[fmt_name], (shape, e1)
         assert np.array_equal(y1, y2)            # run-to-run deterministic
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+@pytest.mark.parametrize("csplit", [2, 4, 8])
+@pytest.mark.parametrize("bn", [64, 128])
+def test_conv_tcgen05_cluster_split_k(torch_cuda, fmt_name, csplit, bn, monkeypatch):
+    """Cluster split-K: the S CTAs of a tile reduce their partial tiles through distributed shared memory and
+    share the epilogue (rows j, j+S, ...).  Every cluster size x N-tile width, ragged M tiles, residual / ReLU,
+    uneven k-block ranges (9 k-blocks over 2 / 4 / 8 CTAs), run-to-run determinism."""
+    torch, lib = torch_cuda
+    monkeypatch.setenv("DEFER_UMMA_FORCE_CSPLIT", str(csplit))
+    monkeypatch.setenv("DEFER_UMMA_BN", str(bn))
+    shapes = [(1, 7, 7, 512, 512, 3, 1, 1), (1, 14, 14, 1024, 256, 1, 1, 0), (1, 56, 56, 64, 64, 3, 1, 1),
+              (2, 14, 14, 1024, 512, 1, 2, 0), (1, 28, 28, 512, 128, 1, 1, 0), (3, 7, 7, 512, 2048, 1, 1, 0)]
+    for i, shape in enumerate(shapes):
+        n, h, w, cin, cout, k, s, pad = shape
+        e1, y1, _ = _conv_case(torch, lib, fmt_name, 2, n, h, w, cin, cout, k, s, pad, relu=(i % 2 == 0), residual=(i % 3 != 1), seed=i)
+        e2, y2, _ = _conv_case(torch, lib, fmt_name, 2, n, h, w, cin, cout, k, s, pad, relu=(i % 2 == 0), residual=(i % 3 != 1), seed=i)
+        assert e1 <= TOL[fmt_name], (shape, csplit, bn, e1)
+        assert np.array_equal(y1, y2)
+
+
+def test_conv_tcgen05_cluster_matches_single_cta(torch_cuda, monkeypatch):
+    """Same inputs through the cluster path and the one-CTA-per-tile path agree to fp32 summation-order noise."""
+    torch, lib = torch_cuda
+    from oracle.keras_ref import rel_err
+    shape = (1, 14, 14, 256, 256, 3, 1, 1)
+    monkeypatch.setenv("DEFER_UMMA_CLUSTER", "0")
+    _, y0, _ = _conv_case(torch, lib, "bf16x2", 2, *shape, True, True, seed=5)
+    monkeypatch.setenv("DEFER_UMMA_CLUSTER", "1")
+    _, y1, _ = _conv_case(torch, lib, "bf16x2", 2, *shape, True, True, seed=5)
+    assert rel_err(y1, y0) <= 1e-5
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+@pytest.mark.parametrize("mode", ["direct", "staged_res_bn64", "staged_bn64"])
+def test_conv_tcgen05_epilogue_variants(torch_cuda, fmt_name, mode, monkeypatch):
+    """The per-thread st.global epilogue (kept for peer-GPU outputs) and the staged TMA epilogue (default) with the
+    residual tile in 64- or 128-wide N tiles give the same answers - bitwise, the arithmetic is identical."""
+    torch, lib = torch_cuda
+    shapes = [(1, 56, 56, 64, 256, 1, 1, 0), (1, 28, 28, 128, 128, 3, 1, 1), (2, 14, 14, 256, 1024, 1, 1, 0),
+              (1, 7, 7, 512, 2048, 1, 1, 0), (1, 56, 56, 256, 512, 1, 2, 0)]
+    ref_y = []
+    for i, shape in enumerate(shapes):
+        _, y, _ = _conv_case(torch, lib, fmt_name, 2, *shape, relu=True, residual=(i != 1), seed=10 + i)
+        ref_y.append(y)
+    if mode == "direct":
+        monkeypatch.setenv("DEFER_UMMA_TMA_EPI", "0")
+    elif mode == "staged_res_bn64":
+        monkeypatch.setenv("DEFER_UMMA_TE_RES_BN64", "1")
+    else:
+        monkeypatch.setenv("DEFER_UMMA_BN", "64")
+    for i, shape in enumerate(shapes):
+        err, y, _ = _conv_case(torch, lib, fmt_name, 2, *shape, relu=True, residual=(i != 1), seed=10 + i)
+        assert err <= TOL[fmt_name], (mode, shape, err)
+        assert np.array_equal(y, ref_y[i]), (mode, shape)
 
 
 @pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])

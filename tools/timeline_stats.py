@@ -38,4 +38,12 @@ print("per-op (ho, k, cout): n CTAs, median / mean lifetime us, share of CTA-tim
 tot = life.sum()
 for tg in np.unique(tag[m]):
     l = (t1 - t0)[m & (tag == tg)] / 1e3
-    print(f"  ho={tg>>20:3d} k={(tg>>16)&15} cout={tg&0xffff:4d}  n={len(l):6d}  med {np.median(l):6.2f}  mean {l.mean():6.2f}  share {l.sum()/tot:5.3f}")
+    sel = m & (tag == tg)
+    extra = ""
+    if a.shape[1] >= 8:
+        php = (a[sel][:, 4:8] - a[sel][:, 0:1]) / 1e3
+        okp = (a[sel][:, 4:8] > 0).all(axis=1)
+        if okp.any():
+            md = np.median(php[okp], axis=0)
+            extra = f"  phases med: setup {md[0]:5.2f} ops {md[1]:5.2f} acc {md[2]:6.2f} epi {md[3]:6.2f}"
+    print(f"  ho={tg>>20:3d} k={(tg>>16)&15} cout={tg&0xffff:4d}  n={len(l):6d}  med {np.median(l):6.2f}  mean {l.mean():6.2f}  share {l.sum()/tot:5.3f}{extra}")
