@@ -140,6 +140,8 @@ struct defer_stage_s {
   };
   std::vector<MegaGroup> groups;
   std::vector<int> op_group;      // group index per op, -1 = launched on its own
+  void* steal_boards = nullptr;   // DEFER_STEAL=1: per-lane ticket boards of the tile-stealing lane kernels
+  bool steal = false;
 
   uint32_t* ctrl_u32(size_t off) { return reinterpret_cast<uint32_t*>(arena + off); }
   uint32_t* ready_flag(int d) { return ctrl_u32(OFF_READY + d * FLAG_STRIDE); }
@@ -236,7 +238,10 @@ static int enqueue_lane(defer_stage_s* s, int lane_id, cudaStream_t st) {
     if (s->has_cons && s->output_writer >= oi && s->output_writer <= span_last)
       DEFER_TRY(launch_wait_flag(s->free_flag(lane_id), s->counter(CTR_WAIT_FREE, lane_id), 1, s->status_ptr(),
                                  s->timeout_ns, st));
-    if (g >= 0) {
+    if (g >= 0 && s->steal) {
+      DEFER_TRY(launch_conv_steal(s->ops[oi].umma.nplanes, s->steal_boards, s->cfg.depth, lane_id, s->groups[g].dev_ops[lane_id],
+                                  span_last - oi + 1, st));
+    } else if (g >= 0) {
       DEFER_TRY(launch_conv_mega(s->ops[oi].umma.nplanes, s->groups[g].dev_ops[lane_id], span_last - oi + 1, st));
     } else {
       DEFER_TRY(launch_op(s, lane_id, oi, st));
@@ -801,7 +806,9 @@ int defer_stage_finalize(defer_stage_t s) {
   s->op_group.assign(s->ops.size(), -1);
   {
     const char* e = getenv("DEFER_MEGA");
-    const bool mega_on = e && atoi(e) != 0;   // cluster-chain megakernel: opt-in (wins only when launch-bound)
+    const char* es = getenv("DEFER_STEAL");
+    s->steal = es && atoi(es) != 0;           // tile-stealing lane kernels: same op grouping, different executor
+    const bool mega_on = (e && atoi(e) != 0) || s->steal;   // cluster-chain megakernel: opt-in (wins only when launch-bound)
     int i = 0, n = (int)s->ops.size();
     while (mega_on && i < n) {
       if (s->ops[i].backend != 2) { ++i; continue; }
@@ -901,6 +908,12 @@ int defer_stage_finalize(defer_stage_t s) {
       s->workspace.push_back(g.dev_ops[l]);
       DEFER_CUDA(cudaMemcpy(g.dev_ops[l], host.data(), ob * n, cudaMemcpyHostToDevice));
     }
+  }
+  if (s->steal && !s->groups.empty()) {
+    const size_t bytes = umma_steal_board_bytes(s->cfg.depth);
+    DEFER_CUDA(cudaMalloc(&s->steal_boards, bytes));
+    s->workspace.push_back(s->steal_boards);
+    DEFER_CUDA(cudaMemset(s->steal_boards, 0, bytes));
   }
   DEFER_CUDA(cudaDeviceSynchronize());
   if (s->cfg.use_graph) {
@@ -1040,6 +1053,7 @@ int defer_stage_num_kernels(defer_stage_t s, int* per_step) {
     auto& op = s->ops[i];
     const int g = s->op_group.empty() ? -1 : s->op_group[i];
     if (g >= 0 && (int)i != s->groups[g].first) continue;   // one launch per megakernel group
+    if (g >= 0 && s->steal) { n += 2; continue; }          // arm + lane kernel
     bool is_memcpy = op.d.kind == DEFER_OP_COPY && s->bufs[op.d.in0].elem == DEFER_BUF_F32 && s->bufs[op.d.out].elem == DEFER_BUF_F32;
     if (!is_memcpy) n += op.n_kernels;
   }

@@ -1,0 +1,21 @@
+#!/bin/bash
+# first GPU call of the next round: validate the opt-in executors, then A/B them against the default
+mkdir -p gpurun_out
+DEFER_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q -x --timeout 120 -k "steal" > gpurun_out/s1_pytest.log 2>&1; tail -n 15 gpurun_out/s1_pytest.log
+B="python bench.py --steps 400 --warmup 20 --no-cpu --no-e2e --no-roofline"
+run() { local name=$1; shift
+  env "$@" timeout 90 $B > gpurun_out/s1_$name.json 2> gpurun_out/s1_$name.err
+  python - "$name" <<'PY'
+import json,sys
+n=sys.argv[1]
+try:
+    d=json.loads(open(f"gpurun_out/s1_{n}.json").read().strip().splitlines()[-1]); print(n, "value", round(d["value"],1))
+except Exception as e:
+    print(n, "FAILED", e, open(f"gpurun_out/s1_{n}.err").read()[-400:])
+PY
+}
+run default
+run steal4 DEFER_STEAL=1 DEFER_STEAL_CTAS=4
+run steal6 DEFER_STEAL=1 DEFER_STEAL_CTAS=6
+run steal9 DEFER_STEAL=1 DEFER_STEAL_CTAS=9
+run mega8 DEFER_MEGA=1 DEFER_MEGA_CLUSTER=8
