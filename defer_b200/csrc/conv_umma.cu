@@ -1221,6 +1221,8 @@ struct alignas(64) LaneBoard {
 };
 static_assert(sizeof(LaneBoard) == 64, "LaneBoard layout");
 
+constexpr unsigned STEAL_OP_DONE = 0xffffu;   // ticket op field of a lane whose run is complete
+
 __host__ __device__ __forceinline__ unsigned long long pack_ticket(unsigned epoch, unsigned op, unsigned tile) {
   return ((unsigned long long)(epoch & 0xffffu) << 48) | ((unsigned long long)(op & 0xffffu) << 32) | tile;
 }
@@ -1251,7 +1253,6 @@ __global__ void steal_arm_kernel(LaneBoard* board, const MegaOp* ops, int n_ops)
 constexpr int STEAL_EPI_WARPS = 8;
 constexpr int STEAL_THREADS = 96 + 32 * STEAL_EPI_WARPS;   // warp 0 TMA+claims, 1 MMA, 2 store/publish, 3..10 epilogue
 constexpr int STEAL_FIFO = 4;
-constexpr unsigned STEAL_OP_DONE = 0xffffu;   // ticket op field of a lane whose run is complete
 
 struct StealDesc {            // one claimed tile (or the stop marker), producer -> consumer roles
   const MegaOp* op;
