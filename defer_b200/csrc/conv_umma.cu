@@ -52,6 +52,7 @@ struct KParams {
   int splits;
   int cluster;                                    // 1: the `splits` CTAs of a tile form one thread-block cluster (DSMEM reduction)
   int tma_epi;                                    // 1: staged epilogue - residual tile in by TMA, finished tile out by TMA store
+  int fast;                                       // opt-in (DEFER_UMMA_FAST): bit 0 scale/shift loads off the setup critical path, bit 1 wait only for the bulk store's smem reads
   int res_stage_bytes;                            // smem reserved for the residual tile (0 without residual / tma_epi)
   int stages;
   uint32_t flags;
@@ -326,17 +327,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // per-channel scale / shift of this CTA's BN columns -> shared memory.  Default: before the setup barrier (every warp
+  // waits for the global loads).  DEFER_UMMA_FAST bit 0: the loads are ISSUED before the barrier but CONSUMED after it,
+  // by the epilogue warps only, so the TMA producer starts its first operand fetch ~0.5 us earlier.
+  float pre_sc = 1.f, pre_sf = 0.f;
+  const int pre_i = threadIdx.x - 64;
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) {
-      int c = c_base + i;
-      s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
-      s_shift[i] = (p.shift && c < p.cout) ? p.shift[c] : 0.f;
+    if (p.fast & 1) {
+      if (pre_i < BN) {          // BN <= 128 = 32 * EW threads at least: one element per thread suffices
+        const int c = c_base + pre_i;
+        if (p.scale && c < p.cout) pre_sc = __ldg(p.scale + c);
+        if (p.shift && c < p.cout) pre_sf = __ldg(p.shift + c);
+      }
+    } else {
+      for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) {
+        int c = c_base + i;
+        s_scale[i] = (p.scale && c < p.cout) ? p.scale[c] : 1.f;
+        s_shift[i] = (p.shift && c < p.cout) ? p.shift[c] : 0.f;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2 && (p.fast & 1)) {
+    if (pre_i < BN) {
+      s_scale[pre_i] = pre_sc;
+      s_shift[pre_i] = pre_sf;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");   // epilogue warps only
+  }
   if (p.pdl) {
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, scale/shift staging,
     // descriptor prefetch) overlapped the tail of the previous kernel of this lane; its outputs are visible
@@ -550,7 +571,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
             tma_store_4d(&tmy1, smem_base + (HALVES + h) * REGION, c_base + 64 * h, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
         }
         bulk_commit();
-        bulk_wait_all();   // the tile is in global memory (and the staging tile is free) before this CTA retires
+        // default: wait until the tile is in global memory.  DEFER_UMMA_FAST bit 1: wait only until the TMA engine has
+        // read the staging tile (what must outlive the CTA); the writes complete before the grid does.
+        if (p.fast & 2) bulk_wait_read0();
+        else bulk_wait_all();
       }
     } else {
     // the residual does not depend on the MMAs: fetch chunk 0 while the main loop is still running
@@ -1617,10 +1641,11 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         __syncwarp();
         if (lane == 0) mbar_arrive(rfree_bar(rb));
       } else if (rbase) {
+        // written by another SM during this kernel's lifetime: read through L2, never from a stale L1 line
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          rh[qq] = *reinterpret_cast<const uint4*>(rbase + c0 + qq * 8);
-          if (NPLANES == 2) rl[qq] = *reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + qq * 8);
+          rh[qq] = __ldcg(reinterpret_cast<const uint4*>(rbase + c0 + qq * 8));
+          if (NPLANES == 2) rl[qq] = __ldcg(reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + qq * 8));
         }
       }
       // ---- accumulator
@@ -2091,6 +2116,8 @@ static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KPara
   kp.cluster = P.cluster;
   kp.stages = P.stages;
   static const int epi_direct = env_int("DEFER_EPILOGUE_DIRECT", 0);
+  static const int fast = env_int("DEFER_UMMA_FAST", 0);
+  kp.fast = fast;
   kp.tma_epi = (P.tma_epi && a.has_out_maps && !a.direct_out && P.splits == 1 && !P.cluster && !epi_direct) ? 1 : 0;
   kp.res_stage_bytes = 0;
   kp.flags = P.flags;

@@ -19,3 +19,6 @@ run steal4 DEFER_STEAL=1 DEFER_STEAL_CTAS=4
 run steal6 DEFER_STEAL=1 DEFER_STEAL_CTAS=6
 run steal9 DEFER_STEAL=1 DEFER_STEAL_CTAS=9
 run mega8 DEFER_MEGA=1 DEFER_MEGA_CLUSTER=8
+run fast1 DEFER_UMMA_FAST=1
+run fast3 DEFER_UMMA_FAST=3
+run bn64_st2 DEFER_UMMA_BN=64 DEFER_UMMA_STAGES=2
