@@ -2116,8 +2116,7 @@ static void fill_kparams(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, KPara
   kp.cluster = P.cluster;
   kp.stages = P.stages;
   static const int epi_direct = env_int("DEFER_EPILOGUE_DIRECT", 0);
-  static const int fast = env_int("DEFER_UMMA_FAST", 0);
-  kp.fast = fast;
+  kp.fast = env_int("DEFER_UMMA_FAST", 0);   // read per launch (launches are captured into graphs once; tests toggle it)
   kp.tma_epi = (P.tma_epi && a.has_out_maps && !a.direct_out && P.splits == 1 && !P.cluster && !epi_direct) ? 1 : 0;
   kp.res_stage_bytes = 0;
   kp.flags = P.flags;

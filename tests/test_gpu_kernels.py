@@ -1,5 +1,6 @@
 """Per-kernel GPU parity through the C-ABI entry points (defer_k_*), torch tensors as containers only."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -338,3 +339,17 @@ def test_stem_kernel_f32_input(torch_cuda):
                                  3, 3, 3, 3, A.FLAG_RELU, None))
         y = _decode(torch, lib, yd, fmt, ref.shape)
         assert R.rel_err(y, ref) <= (5e-3 if fmt_name == "bf16" else 2e-5), fmt_name
+
+
+@pytest.mark.skipif(os.environ.get("DEFER_TEST_EXPERIMENTAL") != "1",
+                    reason="DEFER_UMMA_FAST is opt-in and unvalidated; set DEFER_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("fast", [1, 2, 3])
+def test_conv_tcgen05_fast_flags_bitwise(torch_cuda, fast, monkeypatch):
+    """DEFER_UMMA_FAST only moves loads / relaxes a wait: results must be bit-identical to the default kernel."""
+    torch, lib = torch_cuda
+    shapes = [(1, 56, 56, 64, 256, 1, 1, 0), (1, 14, 14, 256, 256, 3, 1, 1), (1, 7, 7, 2048, 512, 1, 1, 0)]
+    ref = [_conv_case(torch, lib, "bf16x2", 2, *sh, relu=True, residual=(i != 1), seed=20 + i)[1] for i, sh in enumerate(shapes)]
+    monkeypatch.setenv("DEFER_UMMA_FAST", str(fast))
+    for i, sh in enumerate(shapes):
+        err, y, _ = _conv_case(torch, lib, "bf16x2", 2, *sh, relu=True, residual=(i != 1), seed=20 + i)
+        assert err <= TOL["bf16x2"] and np.array_equal(y, ref[i]), (fast, sh)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # first GPU call of the next round: validate the opt-in executors, then A/B them against the default
 mkdir -p gpurun_out
-DEFER_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q -x --timeout 120 -k "steal" > gpurun_out/s1_pytest.log 2>&1; tail -n 15 gpurun_out/s1_pytest.log
+DEFER_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_model.py tests/test_gpu_kernels.py -m gpu -q --timeout 120 -k "steal or fast_flags" > gpurun_out/s1_pytest.log 2>&1; tail -n 15 gpurun_out/s1_pytest.log
 B="python bench.py --steps 400 --warmup 20 --no-cpu --no-e2e --no-roofline"
 run() { local name=$1; shift
   env "$@" timeout 90 $B > gpurun_out/s1_$name.json 2> gpurun_out/s1_$name.err
