@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "steal_board.h"
 
 namespace defer {
 
@@ -1235,44 +1236,11 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
 //   * a lane's kernel leaves when its own lane is complete.
 // Every wait is bounded (mbarrier waits trap after 2 s, the claim loop after 4 s of finding nothing).
 // ==============================================================================================
-struct alignas(64) LaneBoard {
-  unsigned long long ticket;     // [epoch:16 | op:16 | next tile:32]
-  unsigned int done;             // tiles of the current op that are stored
-  unsigned int target_epoch;     // epoch the lane's running kernel works on (set by the arm kernel)
-  const MegaOp* ops;             // this lane's op descriptors for the current run of convs
-  int n_ops;
-  int pad_[9];
-};
+using LaneBoard = LaneBoardT<MegaOp>;   // steal_board.h: the claim / complete protocol (shared with the host model test)
 static_assert(sizeof(LaneBoard) == 64, "LaneBoard layout");
 
-constexpr unsigned STEAL_OP_DONE = 0xffffu;   // ticket op field of a lane whose run is complete
-
-__host__ __device__ __forceinline__ unsigned long long pack_ticket(unsigned epoch, unsigned op, unsigned tile) {
-  return ((unsigned long long)(epoch & 0xffffu) << 48) | ((unsigned long long)(op & 0xffffu) << 32) | tile;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // re-arm one lane for a new run: single thread, stream-ordered before the lane's steal kernel
-__global__ void steal_arm_kernel(LaneBoard* board, const MegaOp* ops, int n_ops) {
-  // Close the lane first: from here on a poller reads STEAL_OP_DONE, and a CAS that still expects an older ticket value
-  // (e.g. the all-zero ticket of a never-armed board read just before this kernel started) fails.
-  const unsigned e = (board->target_epoch + 1u) & 0xffffu;
-  atomicExch(&board->ticket, pack_ticket(e, STEAL_OP_DONE, 0));
-  __threadfence();
-  board->target_epoch = e;
-  board->ops = ops;
-  board->n_ops = n_ops;
-  board->done = 0;
-  __threadfence();
-  st_release_u64(&board->ticket, pack_ticket(e, 0, 0));
-}
+__global__ void steal_arm_kernel(LaneBoard* board, const MegaOp* ops, int n_ops) { steal_arm(board, ops, n_ops); }
 
 constexpr int STEAL_EPI_WARPS = 8;
 constexpr int STEAL_THREADS = 96 + 32 * STEAL_EPI_WARPS;   // warp 0 TMA+claims, 1 MMA, 2 store/publish, 3..10 epilogue
@@ -1360,32 +1328,11 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
       unsigned long long idle_since = 0;
       while (true) {
         // ---- leave once this kernel's own lane is complete
-        {
-          const unsigned long long t = ld_acquire_u64(&mine->ticket);
-          if ((unsigned)(t >> 48) == my_epoch && (unsigned)((t >> 32) & 0xffffu) == STEAL_OP_DONE) break;
-        }
+        if (steal_lane_done(mine, my_epoch)) break;
         // ---- claim a tile: own lane first, then the others
         const MegaOp* op = nullptr;
-        LaneBoard* bd = nullptr;
-        int opi = 0, tile = 0;
-        for (int i = 0; i < n_lanes && op == nullptr; ++i) {
-          int l = my_lane + i;
-          if (l >= n_lanes) l -= n_lanes;
-          LaneBoard* b = boards + l;
-          const unsigned long long t = ld_acquire_u64(&b->ticket);
-          const unsigned e = (unsigned)(t >> 48);
-          if (e != *reinterpret_cast<volatile unsigned int*>(&b->target_epoch)) continue;   // not armed / being re-armed
-          const int o = (int)((t >> 32) & 0xffffu);
-          if (o == (int)STEAL_OP_DONE) continue;                                            // lane finished (until re-armed)
-          if (o >= *reinterpret_cast<volatile int*>(&b->n_ops)) continue;                   // never armed (zeroed board)
-          const MegaOp* cand = *reinterpret_cast<const MegaOp* volatile*>(&b->ops) + o;
-          const unsigned k = (unsigned)(t & 0xffffffffu);
-          if (k >= (unsigned)(cand->m_tiles * cand->n_tiles)) continue;                     // op fully issued, not yet complete
-          if (atomicCAS(&b->ticket, t, t + 1ull) == t) {
-            op = cand; bd = b; opi = o; tile = (int)k;
-          }
-        }
-        if (op == nullptr) {
+        StealClaim cl;
+        if (!steal_try_claim(boards, n_lanes, my_lane, &cl, &op)) {
           const unsigned long long now = gtimer();
           if (idle_since == 0) idle_since = now;
           if (now - idle_since > 4000000000ull) {
@@ -1396,6 +1343,8 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
           __nanosleep(100);
           continue;
         }
+        LaneBoard* bd = boards + cl.lane;
+        const int opi = cl.op, tile = cl.tile;
         idle_since = 0;
         // the ticket was read with acquire: every store of the previous op is visible to this thread; make it
         // visible to the async proxy (TMA) as well
@@ -1552,20 +1501,7 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         }
         mbar_arrive(ofree_bar(buf));                         // staging tile reusable
         // ---- publish: last tile of the op releases the lane's next op
-        __threadfence();
-        const unsigned n_tiles = (unsigned)(op->m_tiles * op->n_tiles);
-        const unsigned prev = atomicAdd(&d.board->done, 1u);
-        if (prev + 1u == n_tiles) {
-          __threadfence();                                   // acquire side of the counter's release sequence
-          d.board->done = 0;
-          const unsigned e = *reinterpret_cast<volatile unsigned int*>(&d.board->target_epoch);
-          const int lane_ops = *reinterpret_cast<volatile int*>(&d.board->n_ops);
-          // the finished state is a sentinel in the ticket itself, so a poller can never mistake a lane that is being
-          // re-armed (new op list, old ticket) for one with claimable work
-          const unsigned next = (d.opi + 1 >= lane_ops) ? STEAL_OP_DONE : (unsigned)d.opi + 1u;
-          __threadfence();
-          st_release_u64(&d.board->ticket, pack_ticket(e, next, 0));
-        }
+        steal_complete(d.board, d.opi, (unsigned)(op->m_tiles * op->n_tiles));
       }
     }
   } else {
