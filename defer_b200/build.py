@@ -18,7 +18,7 @@ def _stale(obj: Path, src: Path) -> bool:
     if not obj.exists():
         return True
     t = obj.stat().st_mtime
-    deps = [src] + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "defer_b200.h"]
+    deps = [src] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "defer_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 
