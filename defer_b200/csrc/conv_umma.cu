@@ -1244,7 +1244,7 @@ __global__ void steal_arm_kernel(LaneBoard* board, const MegaOp* ops, int n_ops)
 
 constexpr int STEAL_EPI_WARPS = 8;
 constexpr int STEAL_THREADS = 96 + 32 * STEAL_EPI_WARPS;   // warp 0 TMA+claims, 1 MMA, 2 store/publish, 3..10 epilogue
-constexpr int STEAL_FIFO = 4;
+constexpr int STEAL_FIFO = 2;   // claimed-tile lookahead per CTA (descriptor slots between the claiming warp and the consumers)
 
 struct StealDesc {            // one claimed tile (or the stop marker), producer -> consumer roles
   const MegaOp* op;
@@ -1329,6 +1329,10 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
       while (true) {
         // ---- leave once this kernel's own lane is complete
         if (steal_lane_done(mine, my_epoch)) break;
+        // ---- a free descriptor slot FIRST (the consumers have picked up tile it - STEAL_FIFO), only then a claim: a CTA
+        // never sits on a claimed tile it cannot start, and runs at most STEAL_FIFO tiles ahead of its store warp
+        const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
+        mbar_wait(qempty_bar(q), (u & 1) ^ 1, error_flag, 21);
         // ---- claim a tile: own lane first, then the others
         const MegaOp* op = nullptr;
         StealClaim cl;
@@ -1353,8 +1357,6 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         const int mt = tile % op->m_tiles, nt = tile / op->m_tiles;
         // ---- publish the descriptor to the consumer roles
         {
-          const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-          mbar_wait(qempty_bar(q), (u & 1) ^ 1, error_flag, 21);
           StealDesc d;
           d.op = op; d.board = bd; d.mt = mt; d.nt = nt; d.opi = opi; d.stop = 0;
           fifo[q] = d;
@@ -2223,7 +2225,9 @@ static int launch_steal_t(void* boards, int n_lanes, int lane, const void* dev_o
     prefer_max_smem(steal_arm_kernel);
     attr_set[dev] = true;
   }
-  int ctas = env_int("DEFER_STEAL_CTAS", 6);                   // CTAs per lane kernel; they serve every armed lane
+  // CTAs per lane kernel; they serve every armed lane.  A steal CTA takes a whole SM (shared memory and ~59 k registers),
+  // so lanes x CTAs should stay below the SM count: the lanes' stem / pool / dense kernels need somewhere to run.
+  int ctas = env_int("DEFER_STEAL_CTAS", 4);
   if (ctas < 1) ctas = 1;
   if (ctas > 148) ctas = 148;
   LaneBoard* b = reinterpret_cast<LaneBoard*>(boards);

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import random
 
-FIFO = 4
+FIFO = 2          # STEAL_FIFO of the kernel (the tests also run 4)
 EPI_WARPS = 8
 
 
@@ -73,8 +73,9 @@ class CTA:
         stage, phase, rit = 0, 0, 0
         for it, (kbs, has_res, direct) in enumerate(self.tiles):
             q, u = it % FIFO, it // FIFO
-            while not self.qempty[q].passed((u & 1) ^ 1):
+            while not self.qempty[q].passed((u & 1) ^ 1):      # slot first, then the claim (kernel order)
                 yield
+            yield                                              # claim attempt(s)
             if self.fifo_readers[q] != 0:
                 raise Violation(f"FIFO slot {q} overwritten with {self.fifo_readers[q]} readers left (tile {it})")
             self.fifo_readers[q] = 2 + EPI_WARPS

@@ -6,8 +6,11 @@ import pytest
 from steal_pipeline_model import Violation, simulate
 
 
+@pytest.mark.parametrize("fifo", [2, 4])
 @pytest.mark.parametrize("stages", [1, 2, 3, 6])
-def test_role_choreography_random_schedules(stages):
+def test_role_choreography_random_schedules(stages, fifo, monkeypatch):
+    import steal_pipeline_model as M
+    monkeypatch.setattr(M, "FIFO", fifo)
     rng = random.Random(100 + stages)
     for trial in range(60):
         n = rng.randint(1, 14)
