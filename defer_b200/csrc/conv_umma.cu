@@ -1249,6 +1249,7 @@ constexpr int STEAL_FIFO = 2;   // claimed-tile lookahead per CTA (descriptor sl
 struct StealDesc {            // one claimed tile (or the stop marker), producer -> consumer roles
   const MegaOp* op;
   LaneBoard* board;
+  long long t_claim;          // %globaltimer at the claim (DEFER_TIMELINE only)
   int mt, nt;
   int opi;
   int stop;
@@ -1359,6 +1360,7 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         {
           StealDesc d;
           d.op = op; d.board = bd; d.mt = mt; d.nt = nt; d.opi = opi; d.stop = 0;
+          d.t_claim = p.timeline ? (long long)gtimer() : 0;
           fifo[q] = d;
           asm volatile("fence.acq_rel.cta;" ::: "memory");
           mbar_arrive(qfull_bar(q));
@@ -1420,7 +1422,7 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
         mbar_wait(qempty_bar(q), (u & 1) ^ 1, error_flag, 22);
         StealDesc d;
-        d.op = nullptr; d.board = nullptr; d.mt = d.nt = d.opi = 0; d.stop = 1;
+        d.op = nullptr; d.board = nullptr; d.mt = d.nt = d.opi = 0; d.stop = 1; d.t_claim = 0;
         fifo[q] = d;
         asm volatile("fence.acq_rel.cta;" ::: "memory");
         mbar_arrive(qfull_bar(q));
@@ -1482,6 +1484,7 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
         const KParams& p = op->p;
         const uint32_t buf = it & 1, ophase = (it >> 1) & 1;
         mbar_wait(ofull_bar(buf), ophase, error_flag, 25);   // all epilogue warps are done with this tile
+        const long long t_epi = p.timeline ? (long long)gtimer() : 0;
         if (!op->direct) {
           int n0 = 0, h0 = 0, w0 = 0;
           if (p.flat) {
@@ -1502,8 +1505,25 @@ conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int 
           asm volatile("fence.proxy.async;" ::: "memory");   // async-proxy writes ordered before the release below
         }
         mbar_arrive(ofree_bar(buf));                         // staging tile reusable
+        const long long t_stored = p.timeline ? (long long)gtimer() : 0;
         // ---- publish: last tile of the op releases the lane's next op
         steal_complete(d.board, d.opi, (unsigned)(op->m_tiles * op->n_tiles));
+        if (p.timeline) {   // DEFER_TIMELINE: one record per TILE (same 8-word format as the per-op kernel's per-CTA records)
+          unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(p.timeline), 1ull);
+          if (slot < (unsigned long long)p.timeline_cap) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* e = p.timeline + 8 + slot * 8;
+            e[0] = d.t_claim;                 // claimed
+            e[1] = (long long)gtimer();       // published
+            e[2] = (long long)smid;
+            e[3] = (long long)p.timeline_tag;
+            e[4] = d.t_claim;                 // (no per-tile setup)
+            e[5] = d.t_claim;
+            e[6] = t_epi;                     // epilogue warps done
+            e[7] = t_stored;                  // bulk store complete
+          }
+        }
       }
     }
   } else {

@@ -22,3 +22,6 @@ run mega8 DEFER_MEGA=1 DEFER_MEGA_CLUSTER=8
 run fast1 DEFER_UMMA_FAST=1
 run fast3 DEFER_UMMA_FAST=3
 run bn64_st2 DEFER_UMMA_BN=64 DEFER_UMMA_STAGES=2
+# per-tile timeline of the steal executor (claim -> epilogue done -> stored -> published), same summary tool
+DEFER_STEAL=1 DEFER_TIMELINE=/tmp/tl_steal.txt timeout 120 $B > gpurun_out/s1_tl_steal.json 2> gpurun_out/s1_tl_steal.err
+python tools/timeline_stats.py /tmp/tl_steal.txt > gpurun_out/s1_tl_steal_stats.txt 2>&1; head -8 gpurun_out/s1_tl_steal_stats.txt
