@@ -65,6 +65,7 @@ PROTOTYPES = {
     "defer_stage_unlink": (_i, [_vp]),
     "defer_stage_finalize": (_i, [_vp]),
     "defer_stage_submit": (_i, [_vp, _u64, _vp, _u64]),
+    "defer_stage_submit_part": (_i, [_vp, _u64, _i, _i, _vp, _u64]),
     "defer_stage_step": (_i, [_vp, _u64]),
     "defer_stage_result": (_i, [_vp, _u64, _vp, _u64]),
     "defer_stage_predict": (_i, [_vp, _vp, _u64, _vp, _u64]),
@@ -73,6 +74,8 @@ PROTOTYPES = {
     "defer_stage_last_step_us": (_i, [_vp, _i, C.POINTER(C.c_float)]),
     "defer_stage_timer_start": (_i, [_vp]),
     "defer_stage_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
+    "defer_stage_mark": (_i, [_vp, _u64, _i]),
+    "defer_stage_mark_elapsed": (_i, [_vp, C.POINTER(C.c_float)]),
     "defer_stage_num_kernels": (_i, [_vp, C.POINTER(_i)]),
     "defer_stage_read_buffer": (_i, [_vp, _i, _i, _vp, _u64]),
     "defer_stage_stream": (_i, [_vp, _i, C.POINTER(_vp)]),

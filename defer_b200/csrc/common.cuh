@@ -178,6 +178,6 @@ int launch_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t st);
 // flag protocol kernels (see stage.cu)
 int launch_wait_flag(const uint32_t* flag, uint32_t* counter, int minus, int* status, unsigned long long timeout_ns,
                      cudaStream_t st);
-int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, cudaStream_t st);
+int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, const int* status, cudaStream_t st);
 
 }  // namespace defer

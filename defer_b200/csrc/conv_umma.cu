@@ -27,7 +27,6 @@
 
 #include "common.cuh"
 #include "conv_umma.cuh"
-#include "steal_board.h"
 
 namespace defer {
 
@@ -1214,481 +1213,6 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
   if (use_cluster) cluster_sync_all();
 }
 
-// ==============================================================================================
-// Tile-stealing lane kernels (opt-in, DEFER_STEAL=1).
-//
-// What the device timeline of the per-op kernels says (profiles/README.md, section 5): at batch 1 a conv CTA owns an SM
-// (~199 KB of shared memory) for ~7 us, of which the K loop is ~40 %; setup, the first TMA round trip and the
-// epilogue are dead time for that SM, and a dependent chain of 52 small launches per lane leaves SMs idle in
-// between.  Here every lane (microbatch in flight) launches ONE kernel of a few persistent CTAs for its whole run of
-// convolutions, and those CTAs take tiles from ANY armed lane:
-//   * per lane a 64-bit ticket in global memory  [epoch:16 | op:16 | next tile:32]  and a completion counter;
-//     a tile is claimed with one atomicCAS (own lane first, then the other lanes round-robin);
-//   * a tile of op o may only be claimed once every tile of op o-1 of that lane is stored: the CTA that completes
-//     the last tile releases the ticket to (epoch, o+1, 0).  Claimed tiles are always finished by their owner, so
-//     a lane whose kernel is resident can always make progress - no CTA ever blocks on another CTA;
-//   * inside a CTA the warp roles run continuously across tiles (the persistent-grid body): warp 0 claims tiles
-//     and streams operands (running ahead by the ring depth), warp 1 issues the MMAs into one of two TMEM
-//     accumulators, warps 3-10 run the staged epilogue, warp 2 issues the TMA stores, waits for their completion and
-//     publishes the tile.  The claim order reaches the consumer roles through a small descriptor FIFO in shared
-//     memory, so the epilogue of tile i, the K loop of tile i+1 and the operand prefetch of tile i+2 overlap even
-//     when the three tiles belong to different lanes;
-//   * a lane's kernel leaves when its own lane is complete.
-// Every wait is bounded (mbarrier waits trap after 2 s, the claim loop after 4 s of finding nothing).
-// ==============================================================================================
-using LaneBoard = LaneBoardT<MegaOp>;   // steal_board.h: the claim / complete protocol (shared with the host model test)
-static_assert(sizeof(LaneBoard) == 64, "LaneBoard layout");
-
-// re-arm one lane for a new run: single thread, stream-ordered before the lane's steal kernel
-__global__ void steal_arm_kernel(LaneBoard* board, const MegaOp* ops, int n_ops) { steal_arm(board, ops, n_ops); }
-
-constexpr int STEAL_EPI_WARPS = 8;
-constexpr int STEAL_THREADS = 96 + 32 * STEAL_EPI_WARPS;   // warp 0 TMA+claims, 1 MMA, 2 store/publish, 3..10 epilogue
-constexpr int STEAL_FIFO = 2;   // claimed-tile lookahead per CTA (descriptor slots between the claiming warp and the consumers)
-
-struct StealDesc {            // one claimed tile (or the stop marker), producer -> consumer roles
-  const MegaOp* op;
-  LaneBoard* board;
-  long long t_claim;          // %globaltimer at the claim (DEFER_TIMELINE only)
-  int mt, nt;
-  int opi;
-  int stop;
-};
-
-template <int NPLANES>
-__global__ void __launch_bounds__(STEAL_THREADS, 1)
-conv_steal_kernel(LaneBoard* __restrict__ boards, int n_lanes, int my_lane, int stages, int* error_flag) {
-  constexpr int BN = MEGA_BN;
-  using L = SmemLayout<NPLANES, BN>;
-  using MS = MegaSmem<NPLANES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t smem_base = smem_u32(smem);
-  const int STAGES = stages;
-  const uint32_t bar_base = smem_base + MS::bar_off(STAGES);
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };        // accumulator b complete
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };   // accumulator b drained
-  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };    // residual tile b landed
-  auto rfree_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };    // residual tile b in registers
-  auto ofull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };    // staging tile b written
-  auto ofree_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 10 + b); };   // staging tile b stored
-  auto qfull_bar = [&](int q) { return bar_base + 8u * (2 * STAGES + 12 + q); };   // descriptor q published
-  auto qempty_bar = [&](int q) { return bar_base + 8u * (2 * STAGES + 12 + STEAL_FIFO + q); };
-  // control block: barriers (<= (2*6 + 12 + 8) * 8 = 256 B), TMEM slot, descriptor FIFO
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MS::bar_off(STAGES) + 256);
-  StealDesc* fifo = reinterpret_cast<StealDesc*>(smem + MS::bar_off(STAGES) + 256 + 16);
-  const uint32_t rbuf_base = smem_base + MS::rbuf_off(STAGES);
-  const uint32_t obuf_base = smem_base + MS::obuf_off(STAGES);
-  uint8_t* rbuf_ptr = smem + MS::rbuf_off(STAGES);
-  uint8_t* obuf_ptr = smem + MS::obuf_off(STAGES);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), STEAL_EPI_WARPS);
-      mbar_init(rfull_bar(b), 1);
-      mbar_init(rfree_bar(b), STEAL_EPI_WARPS);
-      mbar_init(ofull_bar(b), STEAL_EPI_WARPS);
-      mbar_init(ofree_bar(b), 1);
-    }
-    for (int q = 0; q < STEAL_FIFO; ++q) {
-      mbar_init(qfull_bar(q), 1);
-      mbar_init(qempty_bar(q), 2 + STEAL_EPI_WARPS);   // MMA thread, store thread, one per epilogue warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    constexpr uint32_t ncols = MEGA_ACC_BUFS * BN;   // 128
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // =================================================================== claims + TMA producer
-    if (lane == 0) {
-      LaneBoard* mine = boards + my_lane;
-      const unsigned my_epoch = *reinterpret_cast<volatile unsigned int*>(&mine->target_epoch);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t it = 0, rit = 0;
-      unsigned long long idle_since = 0;
-      while (true) {
-        // ---- leave once this kernel's own lane is complete
-        if (steal_lane_done(mine, my_epoch)) break;
-        // ---- a free descriptor slot FIRST (the consumers have picked up tile it - STEAL_FIFO), only then a claim: a CTA
-        // never sits on a claimed tile it cannot start, and runs at most STEAL_FIFO tiles ahead of its store warp
-        const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-        mbar_wait(qempty_bar(q), (u & 1) ^ 1, error_flag, 21);
-        // ---- claim a tile: own lane first, then the others
-        const MegaOp* op = nullptr;
-        StealClaim cl;
-        if (!steal_try_claim(boards, n_lanes, my_lane, &cl, &op)) {
-          const unsigned long long now = gtimer();
-          if (idle_since == 0) idle_since = now;
-          if (now - idle_since > 4000000000ull) {
-            if (error_flag) atomicExch(error_flag, 150);
-            printf("conv_steal: lane %d CTA %d found no work for 4 s\n", my_lane, blockIdx.x);
-            __trap();
-          }
-          __nanosleep(100);
-          continue;
-        }
-        LaneBoard* bd = boards + cl.lane;
-        const int opi = cl.op, tile = cl.tile;
-        idle_since = 0;
-        // the ticket was read with acquire: every store of the previous op is visible to this thread; make it
-        // visible to the async proxy (TMA) as well
-        asm volatile("fence.proxy.async;" ::: "memory");
-        const KParams& p = op->p;
-        const int mt = tile % op->m_tiles, nt = tile / op->m_tiles;
-        // ---- publish the descriptor to the consumer roles
-        {
-          StealDesc d;
-          d.op = op; d.board = bd; d.mt = mt; d.nt = nt; d.opi = opi; d.stop = 0;
-          d.t_claim = p.timeline ? (long long)gtimer() : 0;
-          fifo[q] = d;
-          asm volatile("fence.acq_rel.cta;" ::: "memory");
-          mbar_arrive(qfull_bar(q));
-        }
-        prefetch_tmap(&op->tmx[0]);
-        prefetch_tmap(&op->tmw[0]);
-        int n0 = 0, h0 = 0, w0 = 0;
-        if (p.flat) {
-          w0 = mt * BM;
-        } else {
-          int tw = mt % p.tiles_w;
-          int t2 = mt / p.tiles_w;
-          n0 = (t2 / p.tiles_h) * p.tile_n;
-          h0 = (t2 % p.tiles_h) * p.tile_h;
-          w0 = tw * p.tile_w;
-        }
-        const int c_base = nt * BN;
-        const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
-        const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
-        if (p.res != nullptr && !op->direct) {
-          const uint32_t rb = rit & 1, ur = rit >> 1;
-          ++rit;
-          mbar_wait(rfree_bar(rb), (ur & 1) ^ 1, error_flag, 15);
-          mbar_expect_tx(rfull_bar(rb), NPLANES * a_rows * 128u);
-          const uint32_t dst = rbuf_base + rb * MS::STAGING;
-          tma_load_4d(dst, &op->tmr[0], rfull_bar(rb), c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
-          if (NPLANES == 2)
-            tma_load_4d(dst + BM * 128, &op->tmr[1], rfull_bar(rb), c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
-        }
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 11);
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int khi = tap / p.kw;
-          const int kwi = tap - khi * p.kw;
-          const uint32_t a_dst = smem_base + stage * L::STAGE;
-          const uint32_t b_dst = a_dst + NPLANES * L::A_PLANE;
-          mbar_expect_tx(full_bar(stage), tx_bytes);
-          int cw, ch, cn;
-          if (p.flat) {
-            cw = w0; ch = 0; cn = 0;
-          } else {
-            cw = w0 * p.sw + kwi - p.pad_l;
-            ch = h0 * p.sh + khi - p.pad_t;
-            cn = n0;
-          }
-          tma_load_4d(a_dst, &op->tmx[0], full_bar(stage), cb * BK, cw, ch, cn);
-          tma_load_3d(b_dst, &op->tmw[0], full_bar(stage), cb * BK, c_base, tap);
-          if (NPLANES == 2) {
-            tma_load_4d(a_dst + L::A_PLANE, &op->tmx[1], full_bar(stage), cb * BK, cw, ch, cn);
-            tma_load_3d(b_dst + L::B_PLANE, &op->tmw[1], full_bar(stage), cb * BK, c_base, tap);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        ++it;
-      }
-      // ---- stop marker
-      {
-        const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-        mbar_wait(qempty_bar(q), (u & 1) ^ 1, error_flag, 22);
-        StealDesc d;
-        d.op = nullptr; d.board = nullptr; d.mt = d.nt = d.opi = 0; d.stop = 1; d.t_claim = 0;
-        fifo[q] = d;
-        asm volatile("fence.acq_rel.cta;" ::: "memory");
-        mbar_arrive(qfull_bar(q));
-      }
-    }
-  } else if (warp == 1) {
-    // =================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (uint32_t it = 0;; ++it) {
-        const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-        mbar_wait(qfull_bar(q), u & 1, error_flag, 23);
-        const StealDesc d = fifo[q];
-        mbar_arrive(qempty_bar(q));
-        if (d.stop) break;
-        const int k_blocks = d.op->p.k_blocks;
-        const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 12);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        uint32_t accum = 0;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase, error_flag, 13);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * L::STAGE;
-          const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
-            const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));
-            if (NPLANES == 2) {
-              const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
-              const uint64_t b_lo = make_sw128_desc(b_addr + L::B_PLANE + k * (UMMA_K * 2));
-              umma_bf16(tmem_d, a_lo, b_hi, idesc, accum);
-              accum = 1;
-              umma_bf16(tmem_d, a_hi, b_lo, idesc, accum);
-            }
-            umma_bf16(tmem_d, a_hi, b_hi, idesc, accum);
-            accum = 1;
-          }
-          umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull_bar(buf));
-      }
-    }
-  } else if (warp == 2) {
-    // =================================================================== TMA store + publication
-    if (lane == 0) {
-      for (uint32_t it = 0;; ++it) {
-        const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-        mbar_wait(qfull_bar(q), u & 1, error_flag, 24);
-        const StealDesc d = fifo[q];
-        mbar_arrive(qempty_bar(q));
-        if (d.stop) break;
-        const MegaOp* op = d.op;
-        const KParams& p = op->p;
-        const uint32_t buf = it & 1, ophase = (it >> 1) & 1;
-        mbar_wait(ofull_bar(buf), ophase, error_flag, 25);   // all epilogue warps are done with this tile
-        const long long t_epi = p.timeline ? (long long)gtimer() : 0;
-        if (!op->direct) {
-          int n0 = 0, h0 = 0, w0 = 0;
-          if (p.flat) {
-            w0 = d.mt * BM;
-          } else {
-            int tw = d.mt % p.tiles_w;
-            int t2 = d.mt / p.tiles_w;
-            n0 = (t2 / p.tiles_h) * p.tile_n;
-            h0 = (t2 % p.tiles_h) * p.tile_h;
-            w0 = tw * p.tile_w;
-          }
-          const int c_base = d.nt * BN;
-          const uint32_t src = obuf_base + buf * MS::STAGING;
-          tma_store_4d(&op->tmy[0], src, c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
-          if (NPLANES == 2) tma_store_4d(&op->tmy[1], src + BM * 128, c_base, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
-          bulk_commit();
-          bulk_wait_all();                                   // the tile is in global memory
-          asm volatile("fence.proxy.async;" ::: "memory");   // async-proxy writes ordered before the release below
-        }
-        mbar_arrive(ofree_bar(buf));                         // staging tile reusable
-        const long long t_stored = p.timeline ? (long long)gtimer() : 0;
-        // ---- publish: last tile of the op releases the lane's next op
-        steal_complete(d.board, d.opi, (unsigned)(op->m_tiles * op->n_tiles));
-        if (p.timeline) {   // DEFER_TIMELINE: one record per TILE (same 8-word format as the per-op kernel's per-CTA records)
-          unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(p.timeline), 1ull);
-          if (slot < (unsigned long long)p.timeline_cap) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            long long* e = p.timeline + 8 + slot * 8;
-            e[0] = d.t_claim;                 // claimed
-            e[1] = (long long)gtimer();       // published
-            e[2] = (long long)smid;
-            e[3] = (long long)p.timeline_tag;
-            e[4] = d.t_claim;                 // (no per-tile setup)
-            e[5] = d.t_claim;
-            e[6] = t_epi;                     // epilogue warps done
-            e[7] = t_stored;                  // bulk store complete
-          }
-        }
-      }
-    }
-  } else {
-    // =================================================================== epilogue (warps 3..10)
-    const int ew = warp - 3;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-    const int r = quarter * 32 + lane;
-    const int chalf = ew >> 2;                    // 32-column half of the 64-column accumulator
-    float scv[32], sfv[32];
-    const MegaOp* cached_op = nullptr;
-    int cached_nt = -1;
-    uint32_t rit = 0;
-    for (uint32_t it = 0;; ++it) {
-      const uint32_t q = it % STEAL_FIFO, u = it / STEAL_FIFO;
-      mbar_wait(qfull_bar(q), u & 1, error_flag, 26);
-      const StealDesc d = fifo[q];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qempty_bar(q));
-      if (d.stop) break;
-      const MegaOp* op = d.op;
-      const KParams& p = op->p;
-      const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
-      const int mt = d.mt, nt = d.nt;
-      const int c_base = nt * BN;
-      int n0 = 0, h0 = 0, w0 = 0;
-      if (p.flat) {
-        w0 = mt * BM;
-      } else {
-        int tw0 = mt % p.tiles_w;
-        int t2 = mt / p.tiles_w;
-        n0 = (t2 / p.tiles_h) * p.tile_n;
-        h0 = (t2 % p.tiles_h) * p.tile_h;
-        w0 = tw0 * p.tile_w;
-      }
-      bool valid;
-      size_t pix;
-      row_to_pixel(p, r, n0, h0, w0, valid, pix);
-      const bool relu = p.flags & DEFER_FLAG_RELU;
-      const bool direct = op->direct != 0;
-      const bool has_res = p.res != nullptr;
-      const bool use_rbuf = has_res && !direct;
-      const uint32_t rb = rit & 1, ur = rit >> 1;
-      if (use_rbuf) ++rit;
-      uint8_t* ostg = obuf_ptr + buf * MS::STAGING + r * 128;
-      const uint8_t* rstg = rbuf_ptr + rb * MS::STAGING + r * 128;
-      const int sw = r & 7;
-      const int c0 = chalf * 32;
-      if (op != cached_op || nt != cached_nt) {
-        cached_op = op;
-        cached_nt = nt;
-        const float4* sp = reinterpret_cast<const float4*>(p.scale + c_base + c0);
-        const float4* fp = reinterpret_cast<const float4*>(p.shift + c_base + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 a4 = p.scale ? __ldg(sp + j) : make_float4(1.f, 1.f, 1.f, 1.f);
-          float4 b4 = p.shift ? __ldg(fp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          scv[4 * j] = a4.x; scv[4 * j + 1] = a4.y; scv[4 * j + 2] = a4.z; scv[4 * j + 3] = a4.w;
-          sfv[4 * j] = b4.x; sfv[4 * j + 1] = b4.y; sfv[4 * j + 2] = b4.z; sfv[4 * j + 3] = b4.w;
-        }
-      }
-      // ---- residual of this warp's 32 columns into registers
-      uint4 rh[4], rl[4];
-      const __nv_bfloat16* rbase =
-          (direct && has_res && valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + c_base : nullptr;
-      if (use_rbuf) {
-        mbar_wait(rfull_bar(rb), ur & 1, error_flag, 16);
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const int ch = ((c0 >> 3) + qq) ^ sw;
-          rh[qq] = *reinterpret_cast<const uint4*>(rstg + ch * 16);
-          if (NPLANES == 2) rl[qq] = *reinterpret_cast<const uint4*>(rstg + BM * 128 + ch * 16);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rfree_bar(rb));
-      } else if (rbase) {
-        // written by another SM during this kernel's lifetime: read through L2, never from a stale L1 line
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          rh[qq] = __ldcg(reinterpret_cast<const uint4*>(rbase + c0 + qq * 8));
-          if (NPLANES == 2) rl[qq] = __ldcg(reinterpret_cast<const uint4*>(rbase + p.plane_out + c0 + qq * 8));
-        }
-      }
-      // ---- accumulator
-      mbar_wait(tfull_bar(buf), aphase, error_flag, 14);
-      tc_fence_after();
-      const uint32_t taddr_row = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
-      uint32_t v[32];
-      tmem_ld32(taddr_row + c0, v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));   // this warp's part is in registers: hand the accumulator back
-      const bool add_res = has_res && (use_rbuf || rbase != nullptr);
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(v[j]), scv[j], sfv[j]);
-      if (add_res) {
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh[qq]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[qq * 8 + 2 * e] += __uint_as_float(hw[e] << 16);
-            acc[qq * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u);
-          }
-          if (NPLANES == 2) {
-            const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl[qq]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              acc[qq * 8 + 2 * e] += __uint_as_float(lw[e] << 16);
-              acc[qq * 8 + 2 * e + 1] += __uint_as_float(lw[e] & 0xffff0000u);
-            }
-          }
-        }
-      }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-      }
-      if (!direct) {
-        // staging tile `buf` was last read by the store of tile it-2
-        const uint32_t uo = it >> 1;
-        mbar_wait(ofree_bar(buf), (uo & 1) ^ 1, error_flag, 17);
-      }
-      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.cout + c_base + c0;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        uint4 h, l;
-        uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
-        uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (NPLANES == 2) {
-            split_bf16x2(acc[qq * 8 + 2 * e], acc[qq * 8 + 2 * e + 1], hp[e], lp[e]);
-          } else {
-            hp[e] = pack_bf16x2(acc[qq * 8 + 2 * e], acc[qq * 8 + 2 * e + 1]);
-          }
-        }
-        if (direct) {
-          if (valid) {
-            *reinterpret_cast<uint4*>(yp + qq * 8) = h;
-            if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + qq * 8) = l;
-          }
-        } else {
-          const int ch = ((c0 >> 3) + qq) ^ sw;
-          *reinterpret_cast<uint4*>(ostg + ch * 16) = h;
-          if (NPLANES == 2) *reinterpret_cast<uint4*>(ostg + BM * 128 + ch * 16) = l;
-        }
-      }
-      if (direct) __threadfence_system();   // peer-GPU slot: visible system-wide before the tile is published
-      else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ofull_bar(buf));
-    }
-  }
-
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    constexpr uint32_t ncols = MEGA_ACC_BUFS * BN;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
-  }
-}
-
 // weights: fp32 HWIO [tap][cin][cout]  ->  bf16 [plane][tap][cout][cin]
 __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                                int taps, int cin, int cout, int nplanes) {
@@ -1838,7 +1362,9 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
   P.k_blocks = taps * (cin / 64);
 
   // ---- M tiling
-  P.flat = (kh == 1 && kw == 1 && sh == 1 && sw == 1 && pad_t == 0 && pad_l == 0) ? 1 : 0;
+  // flat [M, C] view only when the output grid IS the input grid (a fused asymmetric ZeroPadding2D gives ho != h even
+  // with pad_t == pad_l == 0; that case takes the 4-D box path, whose out-of-bounds zero fill is the padding)
+  P.flat = (kh == 1 && kw == 1 && sh == 1 && sw == 1 && pad_t == 0 && pad_l == 0 && ho == h && wo == w) ? 1 : 0;
   if (P.flat) {
     long long m = (long long)n * ho * wo;
     P.tile_n = 1; P.tile_h = 1; P.tile_w = BM;
@@ -2218,54 +1744,6 @@ int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStr
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st) {
   int stages = env_int("DEFER_MEGA_STAGES", 3);
   return nplanes == 2 ? launch_mega_t<2>(dev_ops, n_ops, stages, st) : launch_mega_t<1>(dev_ops, n_ops, stages, st);
-}
-
-// ---- tile-stealing lane kernels (DEFER_STEAL=1): host side
-size_t umma_steal_board_bytes(int n_lanes) { return sizeof(LaneBoard) * (size_t)(n_lanes < 1 ? 1 : n_lanes); }
-
-template <int NPLANES>
-static int launch_steal_t(void* boards, int n_lanes, int lane, const void* dev_ops, int n_ops, cudaStream_t st) {
-  using MS = MegaSmem<NPLANES>;
-  using L = SmemLayout<NPLANES, MEGA_BN>;
-  constexpr int CTL = 512;                                     // barriers + TMEM slot + descriptor FIFO
-  constexpr int SMEM_CAP = 227 * 1024 - 1024;
-  int max_stages = (SMEM_CAP - 4 * MS::STAGING - CTL - 1024) / L::STAGE;
-  if (max_stages > 6) max_stages = 6;
-  int stages = env_int("DEFER_STEAL_STAGES", max_stages);
-  if (stages > max_stages) stages = max_stages;
-  if (stages < 1) stages = 1;
-  const size_t smem = (size_t)MS::bar_off(stages) + CTL + 1024;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  DEFER_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    DEFER_CUDA(cudaFuncSetAttribute(conv_steal_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    MS::bar_off(max_stages) + CTL + 1024));
-    prefer_max_smem(conv_steal_kernel<NPLANES>);
-    prefer_max_smem(steal_arm_kernel);
-    attr_set[dev] = true;
-  }
-  // CTAs per lane kernel; they serve every armed lane.  A steal CTA takes a whole SM (shared memory and ~59 k registers),
-  // so lanes x CTAs should stay below the SM count: the lanes' stem / pool / dense kernels need somewhere to run.
-  int ctas = env_int("DEFER_STEAL_CTAS", 4);
-  if (ctas < 1) ctas = 1;
-  if (ctas > 148) ctas = 148;
-  LaneBoard* b = reinterpret_cast<LaneBoard*>(boards);
-  steal_arm_kernel<<<1, 1, 0, st>>>(b + lane, reinterpret_cast<const MegaOp*>(dev_ops), n_ops);
-  DEFER_CUDA(cudaGetLastError());
-  int* err = nullptr;
-  conv_steal_kernel<NPLANES><<<ctas, STEAL_THREADS, smem, st>>>(b, n_lanes, lane, stages, err);
-  DEFER_CUDA(cudaGetLastError());
-  return DEFER_OK;
-}
-
-int launch_conv_steal(int nplanes, void* boards, int n_lanes, int lane, const void* dev_ops, int n_ops, cudaStream_t st) {
-  if (n_ops < 1 || n_ops >= 65535 || lane < 0 || lane >= n_lanes) {
-    set_error("launch_conv_steal: bad arguments (lane %d of %d, %d ops)", lane, n_lanes, n_ops);
-    return DEFER_ERR_INVALID;
-  }
-  return nplanes == 2 ? launch_steal_t<2>(boards, n_lanes, lane, dev_ops, n_ops, st)
-                      : launch_steal_t<1>(boards, n_lanes, lane, dev_ops, n_ops, st);
 }
 
 void umma_conv_release(UmmaConvPlan& P) {

@@ -60,10 +60,6 @@ size_t umma_mega_op_bytes();
 int umma_mega_fill(void* host_dst, const UmmaConvPlan& plan, const UmmaConvLaneArgs& args);   // one op descriptor
 int umma_mega_cluster_size();
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st);
-// Tile-stealing lane kernels (DEFER_STEAL=1): one launch per lane and run of convs; its CTAs claim tiles of ANY armed lane
-// through a ticket board in global memory (`boards`: umma_steal_board_bytes(n_lanes), zero-initialised once per stage).
-size_t umma_steal_board_bytes(int n_lanes);
-int launch_conv_steal(int nplanes, void* boards, int n_lanes, int lane, const void* dev_ops, int n_ops, cudaStream_t st);
 // one op on a persistent grid (same kernel, grid mode): for ops with many tiles
 int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st);
 

@@ -1010,6 +1010,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// Flag protocol of the hop.  A flag holds the number of microbatches signalled so far on that slot (bits 0..30);
+// bit 31 is POISON: a stage whose sticky status is non-zero (its own wait timed out, or it saw poison) signals
+// `count | POISON`, so the failure travels down the chain with the ready flags (and up with the free flags) and the
+// last stage's result call reports it - a stalled peer can never turn into silently wrong results.
+constexpr uint32_t FLAG_POISON = 0x80000000u;
+
 __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t* counter, int minus, int* status,
                                  unsigned long long timeout_ns) {
   if (threadIdx.x != 0) return;
@@ -1018,7 +1024,13 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t* counter, int mi
   if (*reinterpret_cast<volatile int*>(status) != 0) return;  // pipeline already failed: do not spin again
   unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
-  while (ld_acquire_sys(flag) < want) {
+  for (;;) {
+    const uint32_t f = ld_acquire_sys(flag);
+    if (f & FLAG_POISON) {                       // the neighbour failed: inherit the failure
+      atomicExch(status, (int)DEFER_ERR_TIMEOUT);
+      break;
+    }
+    if (f >= want) break;
     if ((++spins & 0x3ff) == 0) {
       if (globaltimer_ns() - t0 > timeout_ns) {
         atomicExch(status, (int)DEFER_ERR_TIMEOUT);
@@ -1029,9 +1041,10 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t* counter, int mi
   }
 }
 
-__global__ void signal_flag_kernel(uint32_t* remote_flag, uint32_t* counter) {
+__global__ void signal_flag_kernel(uint32_t* remote_flag, uint32_t* counter, const int* status) {
   if (threadIdx.x != 0) return;
   uint32_t v = ++(*counter);
+  if (*reinterpret_cast<const volatile int*>(status) != 0) v |= FLAG_POISON;
   __threadfence_system();
   st_release_sys(remote_flag, v);
 }
@@ -1042,8 +1055,8 @@ int launch_wait_flag(const uint32_t* flag, uint32_t* counter, int minus, int* st
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
-int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, cudaStream_t st) {
-  prefer_max_smem(signal_flag_kernel); signal_flag_kernel<<<1, 32, 0, st>>>(remote_flag, counter);
+int launch_signal_flag(uint32_t* remote_flag, uint32_t* counter, const int* status, cudaStream_t st) {
+  prefer_max_smem(signal_flag_kernel); signal_flag_kernel<<<1, 32, 0, st>>>(remote_flag, counter, status);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }

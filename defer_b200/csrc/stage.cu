@@ -106,6 +106,11 @@ struct Lane {
   bool timed = false;
 };
 
+struct Mark {                 // steady-state timing: an event recorded right behind one chosen microbatch
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+
 }  // namespace defer
 
 using namespace defer;
@@ -133,6 +138,7 @@ struct defer_stage_s {
   size_t flush_bytes = 0;
   size_t max_dense_partial = 0;
   cudaEvent_t job_t0 = nullptr, job_t1 = nullptr;
+  Mark marks[2];
   // megakernel groups: runs of consecutive tcgen05 convs executed by one cluster launch per lane
   struct MegaGroup {
     int first = 0, last = 0;
@@ -140,8 +146,6 @@ struct defer_stage_s {
   };
   std::vector<MegaGroup> groups;
   std::vector<int> op_group;      // group index per op, -1 = launched on its own
-  void* steal_boards = nullptr;   // DEFER_STEAL=1: per-lane ticket boards of the tile-stealing lane kernels
-  bool steal = false;
 
   uint32_t* ctrl_u32(size_t off) { return reinterpret_cast<uint32_t*>(arena + off); }
   uint32_t* ready_flag(int d) { return ctrl_u32(OFF_READY + d * FLAG_STRIDE); }
@@ -238,22 +242,19 @@ static int enqueue_lane(defer_stage_s* s, int lane_id, cudaStream_t st) {
     if (s->has_cons && s->output_writer >= oi && s->output_writer <= span_last)
       DEFER_TRY(launch_wait_flag(s->free_flag(lane_id), s->counter(CTR_WAIT_FREE, lane_id), 1, s->status_ptr(),
                                  s->timeout_ns, st));
-    if (g >= 0 && s->steal) {
-      DEFER_TRY(launch_conv_steal(s->ops[oi].umma.nplanes, s->steal_boards, s->cfg.depth, lane_id, s->groups[g].dev_ops[lane_id],
-                                  span_last - oi + 1, st));
-    } else if (g >= 0) {
+    if (g >= 0) {
       DEFER_TRY(launch_conv_mega(s->ops[oi].umma.nplanes, s->groups[g].dev_ops[lane_id], span_last - oi + 1, st));
     } else {
       DEFER_TRY(launch_op(s, lane_id, oi, st));
     }
     if (s->has_prod && s->last_input_reader >= oi && s->last_input_reader <= span_last) {
       uint32_t* remote = reinterpret_cast<uint32_t*>(s->prod_arena + OFF_FREE + lane_id * FLAG_STRIDE);
-      DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_FREE, lane_id), st));
+      DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_FREE, lane_id), s->status_ptr(), st));
     }
   }
   if (s->has_cons) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(s->cons_arena + OFF_READY + lane_id * FLAG_STRIDE);
-    DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_READY, lane_id), st));
+    DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_READY, lane_id), s->status_ptr(), st));
   }
   if (s->cfg.is_last) {
     Lane& L = s->lanes[lane_id];
@@ -629,6 +630,7 @@ int defer_stage_destroy(defer_stage_t s) {
   for (void* p : s->d_weights_bf16) if (p) cudaFree(p);
   if (s->cons_arena && s->cons_is_ipc) cudaIpcCloseMemHandle(s->cons_arena);
   if (s->prod_arena && s->prod_is_ipc) cudaIpcCloseMemHandle(s->prod_arena);
+  for (auto& m : s->marks) if (m.ev) cudaEventDestroy(m.ev);
   if (s->job_t0) cudaEventDestroy(s->job_t0);
   if (s->job_t1) cudaEventDestroy(s->job_t1);
   if (s->flush_buf) cudaFree(s->flush_buf);
@@ -806,9 +808,7 @@ int defer_stage_finalize(defer_stage_t s) {
   s->op_group.assign(s->ops.size(), -1);
   {
     const char* e = getenv("DEFER_MEGA");
-    const char* es = getenv("DEFER_STEAL");
-    s->steal = es && atoi(es) != 0;           // tile-stealing lane kernels: same op grouping, different executor
-    const bool mega_on = (e && atoi(e) != 0) || s->steal;   // cluster-chain megakernel: opt-in (wins only when launch-bound)
+    const bool mega_on = e && atoi(e) != 0;   // cluster-chain megakernel: opt-in (wins only when launch-bound)
     int i = 0, n = (int)s->ops.size();
     while (mega_on && i < n) {
       if (s->ops[i].backend != 2) { ++i; continue; }
@@ -909,12 +909,6 @@ int defer_stage_finalize(defer_stage_t s) {
       DEFER_CUDA(cudaMemcpy(g.dev_ops[l], host.data(), ob * n, cudaMemcpyHostToDevice));
     }
   }
-  if (s->steal && !s->groups.empty()) {
-    const size_t bytes = umma_steal_board_bytes(s->cfg.depth);
-    DEFER_CUDA(cudaMalloc(&s->steal_boards, bytes));
-    s->workspace.push_back(s->steal_boards);
-    DEFER_CUDA(cudaMemset(s->steal_boards, 0, bytes));
-  }
   DEFER_CUDA(cudaDeviceSynchronize());
   if (s->cfg.use_graph) {
     for (int l = 0; l < s->cfg.depth; ++l) {
@@ -940,6 +934,22 @@ int defer_stage_submit(defer_stage_t s, uint64_t seq, const void* host_in, uint6
   DEFER_TRY(set_device(s));
   Lane& L = s->lanes[seq % s->cfg.depth];
   DEFER_CUDA(cudaMemcpyAsync(L.buf[s->cfg.input_buf], host_in, nbytes, cudaMemcpyHostToDevice, L.stream));
+  return DEFER_OK;
+}
+
+int defer_stage_submit_part(defer_stage_t s, uint64_t seq, int index, int count, const void* host_in, uint64_t nbytes) {
+  DEFER_CHECK(s && host_in, "submit_part: null");
+  DEFER_CHECK(s->cfg.is_first, "submit_part: only the first stage takes host input");
+  const Buf& b = s->bufs[s->cfg.input_buf];
+  const size_t sample = b.bytes / (size_t)s->cfg.batch;       // first-stage input is plain fp32 NHWC: samples are contiguous
+  DEFER_CHECK(index >= 0 && count >= 1 && index + count <= s->cfg.batch, "submit_part: samples [%d, %d) outside the microbatch of %d",
+              index, index + count, s->cfg.batch);
+  DEFER_CHECK(nbytes == sample * (size_t)count, "submit_part: got %llu bytes, %d sample(s) are %zu", (unsigned long long)nbytes,
+              count, sample * (size_t)count);
+  DEFER_TRY(set_device(s));
+  Lane& L = s->lanes[seq % s->cfg.depth];
+  DEFER_CUDA(cudaMemcpyAsync((uint8_t*)L.buf[s->cfg.input_buf] + sample * (size_t)index, host_in, nbytes, cudaMemcpyHostToDevice,
+                             L.stream));
   return DEFER_OK;
 }
 
@@ -1045,6 +1055,26 @@ int defer_stage_timer_stop(defer_stage_t s, float* ms) {
   return DEFER_OK;
 }
 
+int defer_stage_mark(defer_stage_t s, uint64_t seq, int slot) {
+  DEFER_CHECK(s && (slot == 0 || slot == 1), "mark: bad arguments");
+  DEFER_TRY(set_device(s));
+  Mark& m = s->marks[slot];
+  if (!m.ev) DEFER_CUDA(cudaEventCreate(&m.ev));
+  DEFER_CUDA(cudaEventRecord(m.ev, s->lanes[seq % s->cfg.depth].stream));
+  m.recorded = true;
+  return DEFER_OK;
+}
+
+int defer_stage_mark_elapsed(defer_stage_t s, float* ms) {
+  DEFER_CHECK(s && ms, "mark_elapsed: null");
+  DEFER_CHECK(s->marks[0].recorded && s->marks[1].recorded, "mark_elapsed: both marks must have been recorded");
+  DEFER_TRY(set_device(s));
+  DEFER_CUDA(cudaEventSynchronize(s->marks[0].ev));
+  DEFER_CUDA(cudaEventSynchronize(s->marks[1].ev));
+  DEFER_CUDA(cudaEventElapsedTime(ms, s->marks[0].ev, s->marks[1].ev));
+  return DEFER_OK;
+}
+
 // ------------------------------------------------------------------------------------------ introspection
 int defer_stage_num_kernels(defer_stage_t s, int* per_step) {
   DEFER_CHECK(s && per_step, "num_kernels: null");
@@ -1053,7 +1083,6 @@ int defer_stage_num_kernels(defer_stage_t s, int* per_step) {
     auto& op = s->ops[i];
     const int g = s->op_group.empty() ? -1 : s->op_group[i];
     if (g >= 0 && (int)i != s->groups[g].first) continue;   // one launch per megakernel group
-    if (g >= 0 && s->steal) { n += 2; continue; }          // arm + lane kernel
     bool is_memcpy = op.d.kind == DEFER_OP_COPY && s->bufs[op.d.in0].elem == DEFER_BUF_F32 && s->bufs[op.d.out].elem == DEFER_BUF_F32;
     if (!is_memcpy) n += op.n_kernels;
   }

@@ -13,7 +13,15 @@ What changed underneath:
   pinned-memory DMA instead of ZFP+LZ4+TCP.
 
 Non-reference additions: ``close()`` / context manager (the reference can only be killed), keyword-only
-``dtype``, ``depth`` (in-flight microbatches) and ``batch``.
+``dtype``, ``depth`` (in-flight microbatches per stage), ``batch`` (samples per queue item; reference: 1) and
+``coalesce``.
+
+Coalescing: the reference's queue items are single images and every node runs them one at a time
+(``src/node.py:103-108``), re-reading its weights per image.  Here up to ``coalesce`` in-flight queue items are
+gathered into ONE engine microbatch (one kernel chain launch per stage, weights streamed once per group); results
+are split back into per-item arrays and delivered in FIFO order, so the API contract (item in, ``(batch, 1000)``
+out, same order) is unchanged.  A group is launched as soon as ``coalesce`` items are there or the input queue has
+been empty for ``linger_us``; unused sample slots of a partial group are computed and dropped.
 """
 from __future__ import annotations
 
@@ -31,13 +39,16 @@ from .node import DTYPE_TO_FMT, StageRunner, parse_device
 
 class DEFER:
     def __init__(self, computeNodes, *, dtype: str = "float32", depth: int = 4, batch: Optional[int] = None,
-                 conv_backend: int = 0, dist=None, wait_timeout_ms: int = 0, max_inflight: int = 0) -> None:
+                 coalesce: int = 1, linger_us: float = 200.0, conv_backend: int = 0, dist=None,
+                 wait_timeout_ms: int = 0, max_inflight: int = 0) -> None:
         self.computeNodes = list(computeNodes)
         self.dispatchIP = "localhost"       # reference: socket.gethostbyname(...) (dispatcher.py:23); no sockets here
         self.chunk_size = 512 * 1000        # kept for interface parity (dispatcher.py:24)
         self.dtype = dtype
         self.depth = int(depth)
-        self.batch = batch
+        self.batch = batch                  # samples per queue item
+        self.coalesce = max(1, int(coalesce))
+        self.linger_s = max(0.0, float(linger_us)) * 1e-6
         self.conv_backend = conv_backend
         self.dist = dist                    # DistContext when launched one-process-per-GPU
         self.wait_timeout_ms = wait_timeout_ms
@@ -49,10 +60,16 @@ class DEFER:
         self._stop = threading.Event()
         self._ready = threading.Event()
         self._inflight: Optional[threading.Semaphore] = None
-        self._submitted = 0
+        self._submitted = 0                 # engine microbatches (groups of <= coalesce items) stepped so far
+        self._group_n: List[int] = []       # items in microbatch seq (ring indexed by seq)
         self._threads: List[threading.Thread] = []
         self._error: Optional[BaseException] = None
-        self.results_delivered = 0
+        self.results_delivered = 0          # queue items delivered
+        self.items_submitted = 0
+
+    @property
+    def engine_batch(self) -> int:
+        return (self.batch or 1) * self.coalesce
 
     # ------------------------------------------------------------------ partition (dispatcher.py:27-42)
     def _partition(self, model: K.Model, layer_parts: List[str]) -> List[K.Model]:
@@ -75,7 +92,7 @@ class DEFER:
         if len(nodeIPs) < len(models):
             raise ValueError(f"{len(models)} stages but only {len(nodeIPs)} compute nodes")
         n = len(models)
-        batch = self.batch or 1
+        batch = self.engine_batch           # samples per engine microbatch = item batch x coalesced items
         if self.dist is not None:
             # one process per GPU: ship (json, weights, next hop) to each rank; ranks build + link themselves
             for i in range(n):
@@ -105,6 +122,8 @@ class DEFER:
     # ------------------------------------------------------------------ ingress (dispatcher.py:85-93)
     def _startDistEdgeInference(self, input: queue.Queue):
         first = self.stages[0] if self.stages else self.dist.local_runner()
+        G, B = self.coalesce, self.batch or 1
+        hold, nh = self._hold, len(self._hold)
         try:
             while not self._stop.is_set():
                 try:
@@ -115,11 +134,33 @@ class DEFER:
                     if self._stop.is_set():
                         return
                 seq = self._submitted
-                x = np.asarray(model_input)
-                if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
-                    x = np.ascontiguousarray(x, dtype=np.float32)
-                self._hold[seq % len(self._hold)] = x   # keep alive until the DMA has certainly happened
-                first.submit(seq, x)
+                n = 0
+                deadline = None
+                while True:
+                    x = np.asarray(model_input)
+                    if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+                        x = np.ascontiguousarray(x, dtype=np.float32)
+                    if x.shape[0] != B:
+                        raise ValueError(f"queue item has batch {x.shape[0]}, DEFER was built for batch {B}")
+                    hold[self.items_submitted % nh] = x      # keep alive until the DMA has certainly happened
+                    self.items_submitted += 1
+                    first.submit_part(seq, n * B, x)
+                    n += 1
+                    if n == G:
+                        break
+                    try:                                     # coalesce whatever is already waiting ...
+                        model_input = input.get_nowait()
+                    except queue.Empty:                      # ... or arrives within the linger window
+                        now = time.perf_counter()
+                        if deadline is None:
+                            deadline = now + self.linger_s
+                        if now >= deadline or self._stop.is_set():
+                            break
+                        try:
+                            model_input = input.get(timeout=deadline - now)
+                        except queue.Empty:
+                            break
+                self._group_n[seq % len(self._group_n)] = n
                 if self.dist is not None:
                     first.step(seq)
                     self.dist.mark_submitted(seq + 1)
@@ -136,6 +177,7 @@ class DEFER:
         try:
             self._ready.wait()
             seq = 0
+            B = self.batch or 1
             local_last = bool(self.stages) or (self.dist is not None and self.dist.world == 1)
             last = (self.stages[-1] if self.stages else self.dist.local_runner()) if local_last else None
             while not self._stop.is_set():
@@ -148,15 +190,19 @@ class DEFER:
                     pred = self.dist.wait_result(seq, self._stop)
                     if pred is None:
                         return
+                    pred = pred.reshape(self.engine_batch, -1)
+                n = self._group_n[seq % len(self._group_n)]
                 self._inflight.release()
                 seq += 1
-                self.results_delivered = seq
-                while not self._stop.is_set():
-                    try:
-                        output.put(pred, timeout=0.05)
-                        break
-                    except queue.Full:
-                        continue
+                for i in range(n):                           # split the group back into queue items, FIFO
+                    item = pred[i * B:(i + 1) * B]
+                    while not self._stop.is_set():
+                        try:
+                            output.put(item, timeout=0.05)
+                            break
+                        except queue.Full:
+                            continue
+                    self.results_delivered += 1
         except BaseException as e:
             self._error = e
             self._stop.set()
@@ -166,10 +212,19 @@ class DEFER:
         if self.batch is None:
             self.batch = 1
         models_to_dispatch = self._partition(model, partition_layers)
+        # the last stage has `depth` result buffers (one process) / the result ring and every stage's lanes bound the
+        # chain (one process per GPU): more microbatches in flight than that would overwrite a result before it is read
+        cap = self.depth * (self.dist.world if self.dist is not None else 1)
+        if self.dist is not None:
+            cap = min(cap, self.dist.ring)
         if self.max_inflight <= 0:
-            self.max_inflight = self.depth * (self.dist.world if self.dist is not None else 1)
+            self.max_inflight = cap
+        elif self.max_inflight > cap:
+            raise ValueError(f"max_inflight {self.max_inflight} exceeds what the pipeline can hold ({cap} = depth "
+                             f"{self.depth} x {'ranks' if self.dist is not None else '1'}, result ring included)")
         self._inflight = threading.Semaphore(self.max_inflight)
-        self._hold = [None] * (2 * self.max_inflight + 2)
+        self._hold = [None] * ((2 * self.max_inflight + 2) * self.coalesce)
+        self._group_n = [0] * (2 * self.max_inflight + 2)
         a = threading.Thread(target=self._result_server, args=(output_stream,), name="defer-result")
         a.start()
         try:
@@ -200,6 +255,18 @@ class DEFER:
                 t.join(timeout=10)
         if self.dist is not None:
             self.dist.request_stop()
+        # Stages write into each other's arenas (outputs + ready flags downstream, free flags upstream): first let
+        # EVERY stage finish what is enqueued, then drop every cross-stage mapping, and only then free memory.
+        for r in self.stages:
+            try:
+                r.sync()
+            except Exception:
+                pass
+        for r in self.stages:
+            try:
+                r.unlink()
+            except Exception:
+                pass
         for r in self.stages:
             r.close()
         self.stages = []

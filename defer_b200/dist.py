@@ -19,7 +19,7 @@ from typing import List, Optional
 
 import numpy as np
 
-_HDR_WORDS = 16     # uint64 header: [0] submitted, [1] stop, [2] done, [3] ready ranks, [4] out_elems, [5] ring
+_HDR_WORDS = 16     # uint64 header: [0] submitted, [1] stop, [2] done (published), [6] consumed by the dispatcher
 
 
 class DistContext:
@@ -167,8 +167,13 @@ class DistContext:
         return bool(self.hdr[1])
 
     def publish_result(self, seq: int, out: np.ndarray):
+        # never run more than `ring` rows ahead of the dispatcher's result thread (it would overwrite unread rows)
+        while seq - int(self.hdr[6]) >= self.ring:
+            if self.stop_requested():
+                return
+            time.sleep(20e-6)
         self.results[seq % self.ring, :] = out.reshape(-1)
-        self.hdr[2] = seq + 1          # x86 TSO: the row is visible before the counter
+        self.hdr[2] = seq + 1          # x86-64 (TSO): the row's stores are globally visible before the counter's
 
     def done(self) -> int:
         return int(self.hdr[2])
@@ -184,7 +189,9 @@ class DistContext:
                 time.sleep(10e-6)
             if time.perf_counter() - t0 > timeout:
                 raise TimeoutError(f"result {seq} not published within {timeout}s")
-        return np.array(self.results[seq % self.ring], copy=True)
+        row = np.array(self.results[seq % self.ring], copy=True)
+        self.hdr[6] = seq + 1          # row copied out: the publisher may reuse it
+        return row
 
     def close(self):
         try:

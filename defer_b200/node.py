@@ -64,6 +64,7 @@ class StageRunner:
         self.is_first, self.is_last = bool(is_first), bool(is_last)
         self.handle = C.c_void_p()
         self._pinned: Dict[int, tuple] = {}
+        self._marks: Dict[int, int] = {}
         self._streams = 0
         if not (is_first and is_last):
             used = _STREAMS_PER_DEVICE.get(self.device, 0)
@@ -146,8 +147,31 @@ class StageRunner:
             raise ValueError(f"{self.name}: input shape {tuple(x.shape)} != stage input {self.in_shape}")
         A.check(self.lib.defer_stage_submit(self.handle, seq, x.ctypes.data, x.nbytes))
 
+    def submit_part(self, seq: int, index: int, x: np.ndarray) -> None:
+        """Coalesced ingress: copy the queue item ``x`` (``k`` samples, usually 1 - ``test/test.py:22``) into samples
+        ``[index, index + k)`` of microbatch ``seq``.  Same lifetime rule as ``submit``."""
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            self._keep = x
+        if tuple(x.shape[1:]) != self.in_shape[1:]:
+            raise ValueError(f"{self.name}: item shape {tuple(x.shape)} does not match stage input {self.in_shape}")
+        A.check(self.lib.defer_stage_submit_part(self.handle, seq, index, x.shape[0], x.ctypes.data, x.nbytes))
+
     def step(self, seq: int) -> None:
         A.check(self.lib.defer_stage_step(self.handle, seq))
+        if self._marks:
+            slot = self._marks.pop(seq, None)
+            if slot is not None:
+                A.check(self.lib.defer_stage_mark(self.handle, seq, slot))
+
+    def mark_after(self, seq: int, slot: int) -> None:
+        """Steady-state timing: record timing event ``slot`` (0 | 1) right behind microbatch ``seq`` when it is stepped."""
+        self._marks[int(seq)] = int(slot)
+
+    def mark_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        A.check(self.lib.defer_stage_mark_elapsed(self.handle, C.byref(ms)))
+        return ms.value
 
     def result(self, seq: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

@@ -149,6 +149,10 @@ DEFER_API int defer_stage_finalize(defer_stage_t s);
 /* ---- steady state  (replaces the recv -> predict -> send loop, src/node.py:88-91,103-108) --- */
 /* First stage only: enqueue the H2D copy of microbatch `seq` from host memory (pinned => async). */
 DEFER_API int defer_stage_submit(defer_stage_t s, uint64_t seq, const void* host_in, uint64_t nbytes);
+/* First stage only, coalesced ingress: the reference's queue items are single samples (test/test.py:22,47-49); a stage
+ * built with batch = G x item-batch runs G in-flight items per launch.  Copies `count` consecutive samples of
+ * microbatch `seq`, starting at sample `index`, from host memory (nbytes = count x bytes of one sample). */
+DEFER_API int defer_stage_submit_part(defer_stage_t s, uint64_t seq, int index, int count, const void* host_in, uint64_t nbytes);
 /* Enqueue microbatch `seq` on lane seq % depth: wait-input -> kernel chain -> hop -> flags. Async. */
 DEFER_API int defer_stage_step(defer_stage_t s, uint64_t seq);
 /* Last stage only: block until microbatch `seq` is complete and copy its fp32 output to host. */
@@ -166,6 +170,13 @@ DEFER_API int defer_stage_last_step_us(defer_stage_t s, int lane, float* us);
  * lane 0 wait for every lane, records T1, synchronises and returns T1 - T0 in milliseconds. */
 DEFER_API int defer_stage_timer_start(defer_stage_t s);
 DEFER_API int defer_stage_timer_stop(defer_stage_t s, float* ms);
+
+/* Steady-state timing without draining the pipeline (the reference protocol counts results inside a window while the
+ * chain stays flooded, test/test.py:25-36): call mark(seq, slot) right after step(seq); it records a CUDA event behind
+ * that microbatch on its lane.  mark_elapsed = device time from the completion of the slot-0 microbatch to the
+ * completion of the slot-1 microbatch. */
+DEFER_API int defer_stage_mark(defer_stage_t s, uint64_t seq, int slot /* 0 | 1 */);
+DEFER_API int defer_stage_mark_elapsed(defer_stage_t s, float* ms);
 
 /* ---- introspection for tests and benches --------------------------------------------------- */
 DEFER_API int defer_stage_num_kernels(defer_stage_t s, int* per_step);           /* kernel launches per step */

@@ -341,8 +341,6 @@ def test_stem_kernel_f32_input(torch_cuda):
         assert R.rel_err(y, ref) <= (5e-3 if fmt_name == "bf16" else 2e-5), fmt_name
 
 
-@pytest.mark.skipif(os.environ.get("DEFER_TEST_EXPERIMENTAL") != "1",
-                    reason="DEFER_UMMA_FAST is opt-in and unvalidated; set DEFER_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("fast", [1, 2, 3])
 def test_conv_tcgen05_fast_flags_bitwise(torch_cuda, fast, monkeypatch):
     """DEFER_UMMA_FAST only moves loads / relaxes a wait: results must be bit-identical to the default kernel."""
@@ -353,3 +351,30 @@ def test_conv_tcgen05_fast_flags_bitwise(torch_cuda, fast, monkeypatch):
     for i, sh in enumerate(shapes):
         err, y, _ = _conv_case(torch, lib, "bf16x2", 2, *sh, relu=True, residual=(i != 1), seed=20 + i)
         assert err <= TOL["bf16x2"] and np.array_equal(y, ref[i]), (fast, sh)
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+def test_conv_tcgen05_1x1_with_bottom_right_padding(torch_cuda, fmt_name):
+    """A fused asymmetric ZeroPadding2D(((0, 1), (0, 2))) in front of a 1x1 'valid' conv: pad_t == pad_l == 0 but the
+    output grid is larger than the input grid, so the flat [M, C] fast path must NOT be taken."""
+    torch, lib = torch_cuda
+    from oracle import keras_ref as R
+    fmt = FMTS[fmt_name]
+    rng = np.random.default_rng(31)
+    n, h, w, cin, cout = 2, 13, 14, 64, 128
+    pb, pr = 1, 2
+    x = rng.standard_normal((n, h, w, cin), dtype=np.float32)
+    wk = rng.standard_normal((1, 1, cin, cout), dtype=np.float32) * np.float32(np.sqrt(2.0 / cin))
+    shift = (rng.standard_normal(cout) * 0.2).astype(np.float32)
+    xq, wq = _quantise(x, fmt), _quantise(wk, fmt)
+    ref = R.conv2d(np.pad(xq.astype(np.float64), ((0, 0), (0, pb), (0, pr), (0, 0))), wq.astype(np.float64), None, (1, 1), "valid")
+    ref = ref + shift.astype(np.float64)
+    xd = _encode(torch, lib, x, fmt)
+    wd, fd = torch.from_numpy(wk).cuda(), torch.from_numpy(shift).cuda()
+    yd = _alloc_act(torch, fmt, ref.size)
+    A.check(lib.defer_k_conv(fmt, 2, _ptr(xd), 0, _ptr(wd), None, _ptr(fd), None, _ptr(yd), n, h, w, cin, cout, 1, 1, 1, 1,
+                             0, 0, pb, pr, 0, None))
+    torch.cuda.synchronize()
+    y = _decode(torch, lib, yd, fmt, ref.shape)
+    assert R.rel_err(y, ref) <= TOL[fmt_name]
+    assert np.allclose(y[:, h:, :, :], shift, atol=1e-2)      # the padded rows / columns see only the shift

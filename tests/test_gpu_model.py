@@ -214,34 +214,75 @@ def test_unfused_cut_points_on_gpu(resnet50, x224):
     assert _rel(outs[0], ref) <= 1e-3
 
 
-# Opt-in executors that were written after the round's GPU budget was spent: not yet validated on hardware, hence
-# not part of the default `-m gpu` run.  DEFER_TEST_EXPERIMENTAL=1 enables them (tools/r2_steal_check.sh).
-EXPERIMENTAL = os.environ.get("DEFER_TEST_EXPERIMENTAL") == "1"
+def test_stalled_upstream_poisons_the_chain(resnet50, x224):
+    """A stage whose input never arrives times out on the device; the failure must travel down the chain with the
+    ready flags (poison bit) so the LAST stage's result call reports it instead of delivering garbage."""
+    cuts = applications.default_cuts(resnet50, 4)[:2]
+    names = ["input_1"] + cuts + [resnet50.output._keras_history[0].name]
+    parts = [dag_util.construct_model(resnet50, names[i], names[i + 1], part_name=f"part{i+1}") for i in range(3)]
+    runners = [StageRunner.from_wire(p.to_json(), p.get_weights(), device=0, dtype="float32", max_batch=1, depth=2,
+                                     is_first=(i == 0), is_last=(i == 2), finalize=False, wait_timeout_ms=300)
+               for i, p in enumerate(parts)]
+    try:
+        for i in range(2):
+            runners[i].link_to(runners[i + 1])
+        for r in runners:
+            r.finalize()
+        # healthy microbatch first
+        runners[0].submit(0, x224)
+        for r in runners:
+            r.step(0)
+        y = runners[2].result(0)
+        assert _rel(y, _oracle(resnet50, x224)) <= 1e-3
+        # now the first stage "dies": only stages 1 and 2 are stepped
+        runners[1].step(1)
+        runners[2].step(1)
+        with pytest.raises(A.DeferError) as ei:
+            runners[2].result(1)
+        assert ei.value.code == A.ERR_TIMEOUT
+        with pytest.raises(A.DeferError):
+            runners[1].status()
+        with pytest.raises(A.DeferError):
+            runners[2].status()
+        runners[0].status()          # the stage that was never stepped has nothing to report
+    finally:
+        for r in runners:
+            try:
+                r.sync()
+            except Exception:
+                pass
+        for r in runners:
+            r.unlink()
+        for r in runners:
+            r.close()
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="DEFER_STEAL path is opt-in and unvalidated; set DEFER_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
-def test_steal_lane_kernels_match_per_op(resnet50, x224, dtype, monkeypatch):
-    """Tile-stealing lane kernels (DEFER_STEAL=1): 4 lanes in flight so tiles really are taken across lanes; every
-    item of the same input must give the same answer, equal to the per-op kernels' within summation-order noise and to
-    the oracle within the parity bar."""
-    outs = {}
-    for steal in ("1", "0"):
-        monkeypatch.setenv("DEFER_STEAL", steal)
-        outs[steal] = _pipeline_on_one_gpu(resnet50, [], x224, dtype, depth=4, n_items=12)
-    ref = _oracle(resnet50, x224)
-    for y in outs["1"]:
-        assert np.array_equal(y, outs["1"][0])
-        assert _rel(y, ref) <= TOL[dtype]
-    assert _rel(outs["1"][0], outs["0"][0]) <= (1e-4 if dtype == "float32" else 2e-2)
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="DEFER_STEAL path is opt-in and unvalidated; set DEFER_TEST_EXPERIMENTAL=1")
-def test_steal_lane_kernels_in_a_pipeline(resnet50, x224, monkeypatch):
-    """Same executor with the hop: the last conv of a stage writes the next stage's slot with direct stores."""
-    monkeypatch.setenv("DEFER_STEAL", "1")
-    outs = _pipeline_on_one_gpu(resnet50, ["add_4", "add_9"], x224, "float32", depth=3, n_items=9)
-    ref = _oracle(resnet50, x224)
-    for y in outs:
-        assert np.array_equal(y, outs[0])
-        assert _rel(y, ref) <= 1e-3
+@pytest.mark.parametrize("coalesce", [4, 8])
+def test_defer_coalesced_items_fifo_and_parity(resnet50, x224, coalesce):
+    """Coalesced ingress on the GPU: single-image queue items, `coalesce` of them per launch, per-item results in FIFO
+    order, each within the parity bar; an item's answer does not depend on its position inside the group."""
+    from defer_b200 import DEFER
+    n_dev = A.device_count()
+    cuts = applications.default_cuts(resnet50, 2)
+    defer = DEFER([i % n_dev for i in range(2)], dtype="float32", depth=2, coalesce=coalesce, linger_us=3000,
+                  wait_timeout_ms=5000)
+    in_q, out_q = queue.Queue(), queue.Queue()
+    t = threading.Thread(target=defer.run_defer, args=(resnet50, cuts, in_q, out_q), daemon=True)
+    t.start()
+    try:
+        assert defer.wait_ready(300)
+        xs = [x224 * np.float32(1.0 + 0.1 * i) for i in range(3)]
+        refs = [_oracle(resnet50, x) for x in xs]
+        n = 3 * coalesce + 5                      # the last group is partial
+        for i in range(n):
+            in_q.put(xs[i % 3])
+        outs = [out_q.get(timeout=120) for _ in range(n)]
+        for i, y in enumerate(outs):
+            assert y.shape == (1, 1000)
+            assert _rel(y, refs[i % 3]) <= 1e-3, i
+        for i in range(3, n):                     # same image => same bits wherever it sat in its group
+            assert np.array_equal(outs[i], outs[i % 3]), i
+    finally:
+        defer.close()
+        t.join(timeout=30)
+    assert not t.is_alive()
