@@ -270,8 +270,11 @@ def run_b200(args):
         args.gpus = world
     n_stages = args.gpus
     G = args.coalesce or DEFAULT_COALESCE[args.model]
-    depth = args.depth or DEFAULT_DEPTH
     K, W, B = args.steps, max(args.warmup, 3), args.batch
+    # Lanes complete in round-robin bursts; the window [completion of W-1, completion of W+K-1] is exactly K steps of
+    # steady state only when both marks sit on the same lane, i.e. K % depth == 0: auto depth = largest divisor of K
+    # that is <= DEFAULT_DEPTH (an explicit --depth is honoured and reported as aligned or not).
+    depth = args.depth or max(d for d in range(1, DEFAULT_DEPTH + 1) if K % d == 0)
     EB = G * B                                  # samples per engine microbatch
 
     ctx = None
@@ -474,7 +477,7 @@ def run_b200(args):
         return rows
 
     def roofline_of(rows, batch):
-        conv = [r for r in rows if r["kernel"].startswith("conv_umma") or r["kernel"].startswith("conv_mega")]
+        conv = [r for r in rows if any(k in r["kernel"] for k in ("conv_umma", "conv_mega", "conv_stream")) and "stem" not in r["kernel"]]
         if not conv:
             conv = [r for r in rows if r["kernel"].startswith("conv")]
         groups = {}
@@ -574,6 +577,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": {"float32": "bf16x3->f32", "float32_simt": "f32", "bfloat16": "bf16"}[args.dtype],
                 "data": "synthetic", "config": workload_config(args),
                 "engine": {"coalesce": G, "images_per_step": EB, "depth": depth, "max_inflight": max_inflight,
+                           "window_lane_aligned": K % depth == 0,
                            "preflood_steps": P, "tail_steps": T, "cuts": cut_info,
                            "step": "one pass of the N-stage hot path over one coalesced group of G single-image queue items"},
                 "clocks": clocks, "gpu_launches": launches,

@@ -251,6 +251,19 @@ __device__ __forceinline__ void row_to_pixel(const KParams& p, int r, int n0, in
 
 // ---------------------------------------------------------------------------------------------- the kernel
 // EW = epilogue warps: 4 (192 threads, 2 CTAs/SM) or 8 (320 threads, 1 CTA/SM; warp pairs split the columns)
+// TMEM -> registers for 32 accumulator columns of the fp32-parity scheme with the 2*BN-row B operand: the hi-term block
+// [0, BN) plus the a_hi x b_lo block [BN, 2BN) of the same output columns (see conv_stream_kernel)
+template <int NPLANES, int BN>
+__device__ __forceinline__ void tmem_ld32_acc(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld32(taddr, v);
+  if constexpr (NPLANES == 2) {
+    uint32_t v2[32];
+    tmem_ld32(taddr + BN, v2);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(v2[q]));
+  }
+}
+
 template <int NPLANES, int BN, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
@@ -322,7 +335,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    constexpr uint32_t ncols = BN < 32 ? 32 : BN;
+    constexpr uint32_t ncols = (NPLANES == 2 ? 2 : 1) * (BN < 32 ? 32 : BN);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -422,6 +435,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
     // =================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
+      constexpr uint32_t idesc_wide = make_idesc<(NPLANES == 2 ? 2 * BN : BN)>();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accum = 0;
@@ -435,15 +449,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
-          const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));
+          const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));   // NPLANES == 2: the 2*BN rows [b_hi | b_lo]
           if (NPLANES == 2) {
+            // two instructions per K step instead of three (tcgen05.mma costs ~100 cycles whatever N is): the weight
+            // planes are adjacent in shared memory, so a_hi x [b_hi | b_lo] fills columns [0,BN) and [BN,2BN) at once
             const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
-            const uint64_t b_lo = make_sw128_desc(b_addr + L::B_PLANE + k * (UMMA_K * 2));
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, accum);   // small terms first
-            accum = 1;
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, accum);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc_wide, accum);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+          } else {
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, accum);
           }
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, accum);
           accum = 1;
         }
         umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
@@ -476,7 +491,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr_row + c0, v);   // warp-collective
+        tmem_ld32_acc<NPLANES, BN>(taddr_row + c0, v);   // warp-collective
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) sts4(red_row + (uint32_t)(c0 + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -503,7 +518,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr_row + c0, v);   // warp-collective
+        tmem_ld32_acc<NPLANES, BN>(taddr_row + c0, v);   // warp-collective
         if (!valid) continue;
         const int half = c0 >> 6;
         const int chb = (c0 & 63) >> 3;            // first 16-B chunk of this 32-column group inside its 128-B row
@@ -606,7 +621,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr_row + c0, v);
+        tmem_ld32_acc<NPLANES, BN>(taddr_row + c0, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           __stcg(reinterpret_cast<float4*>(mine + c0 + j),
@@ -646,7 +661,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
           }
         } else {
           uint32_t v[32];
-          tmem_ld32(taddr_row + c0, v);   // warp-collective: every lane takes part, stores are masked below
+          tmem_ld32_acc<NPLANES, BN>(taddr_row + c0, v);   // warp-collective: every lane takes part, stores are masked below
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
         }
@@ -785,7 +800,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
   }
   if (warp == 1) {
     tc_fence_after();
-    constexpr uint32_t ncols = BN < 32 ? 32 : BN;
+    constexpr uint32_t ncols = (NPLANES == 2 ? 2 : 1) * (BN < 32 ? 32 : BN);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -1213,6 +1228,420 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
   if (use_cluster) cluster_sync_all();
 }
 
+// ==============================================================================================
+// Streaming persistent convolution kernel (round 2): the executor of every conv with enough tiles.
+//
+// Measured on B200 (tools/microbench/fill_bench.cu, profiles/r02_fill_bench.txt): TMA delivers ~14 TB/s of
+// L2-resident tiles into shared memory chip-wide (~97 GB/s per SM) when ~190 KB are in flight per SM, but the round
+// trip under load is ~2 us - a CTA's fill rate is (operand bytes in flight) / 2 us.  The round-1 persistent kernel
+// kept 128 KB of its shared memory as epilogue staging and only 2 x 48 KB in flight: 48 GB/s per SM, 6-7 TB/s
+// chip-wide - the number every conv launch was stuck at.  This kernel gives the shared memory to the operand ring:
+//   * ring of S stages x (A 128 x 64 + B BN x 64, all planes); BN = 64 or 128 (one N = BN MMA per k-step);
+//   * epilogue staging is U small "units" (one 64-column chunk of a tile, all planes: 32 KB fp32-parity / 16 KB
+//     bf16).  A unit serves BOTH directions: the residual chunk is TMA-loaded INTO it, the epilogue warps read it,
+//     add and overwrite it in place, and one TMA store ships it out;
+//   * S and U are chosen per op at run time: K-heavy ops get S x STAGE ~ 190 KB and one unit, output-heavy ops
+//     (1 - 4 k-blocks per tile) get a short ring and 3 - 4 units so residual fetch, math and store of successive
+//     chunks overlap.
+//   * tcgen05.mma has a ~100-cycle floor per instruction on B200 whatever N is (measured with the phase trace: 12
+//     instructions per k-block take 1200 cycles for N = 64 and for N = 128 alike), so the fp32-parity path issues TWO
+//     instructions per K = 16 step instead of three: the hi and lo planes of the weights sit back to back in shared
+//     memory and act as ONE 2*BN-row B operand,  a_hi x [b_hi | b_lo] -> accumulator columns [0, BN) and [BN, 2BN),
+//     then a_lo x b_hi -> columns [0, BN); the epilogue adds the two column blocks (hi*lo is the small term).
+// Warp roles (352 threads): warp 0 operand producer (TMA), warp 1 MMA issuer (two TMEM accumulators of BN columns),
+// warp 2 chunk manager (residual loads, TMA stores, bulk-group bookkeeping), warps 3-10 epilogue math.
+// All roles walk the same (tile, chunk) sequence; every wait is bounded (mbar_wait traps after 2 s).
+// ==============================================================================================
+constexpr int STREAM_EPI_WARPS = 8;
+constexpr int STREAM_THREADS = 96 + 32 * STREAM_EPI_WARPS;   // 352
+constexpr int STREAM_CTL_BYTES = 512;
+constexpr int STREAM_MAX_UNITS = 4;
+
+template <int NPLANES, int BN>
+struct StreamSmem {
+  using L = SmemLayout<NPLANES, BN>;
+  static constexpr int UNIT = NPLANES * BM * 128;            // one 64-column chunk of an output tile, all planes
+  __host__ __device__ static constexpr int unit_off(int stages) { return stages * L::STAGE; }
+  __host__ __device__ static constexpr int ctl_off(int stages, int units) { return stages * L::STAGE + units * UNIT; }
+  __host__ __device__ static constexpr int total(int stages, int units) { return ctl_off(stages, units) + STREAM_CTL_BYTES + 1024; }
+};
+
+template <int NPLANES, int BN>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* error_flag) {
+  using L = SmemLayout<NPLANES, BN>;
+  using SS = StreamSmem<NPLANES, BN>;
+  constexpr int CH = BN / 64;                      // 64-column chunks per tile
+  constexpr int ACC_COLS = NPLANES == 2 ? 2 * BN : BN;   // TMEM columns of one accumulator (fp32 parity: [hi-terms | a_hi x b_lo])
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int STAGES = stages, U = units;
+  const uint32_t bar_base = smem_base + SS::ctl_off(STAGES, U);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                      // [0, 8)
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };               // [8, 16)
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  auto ready_bar = [&](int u) { return bar_base + 8u * (20 + u); };              // unit holds the residual / may be written
+  auto done_bar = [&](int u) { return bar_base + 8u * (24 + u); };               // unit holds the finished chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, U) + 8 * 28);
+  const uint32_t unit_base = smem_base + SS::unit_off(STAGES);
+  uint8_t* unit_ptr = smem + SS::unit_off(STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const MegaOp& op = *opp;
+  const KParams& p = op.p;
+  const int n_tiles = op.m_tiles * op.n_tiles;     // n_tiles counted in BN-wide column blocks (host: cout / BN)
+  const int rank = (int)blockIdx.x, csize = (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), STREAM_EPI_WARPS);
+    }
+    for (int u = 0; u < U; ++u) {
+      mbar_init(ready_bar(u), 1);
+      mbar_init(done_bar(u), STREAM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    constexpr uint32_t ncols = 2 * ACC_COLS;         // two accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // optional phase trace (DEFER_UMMA_TRACE through defer_k_conv): CTA 0 stamps %globaltimer at role milestones of its
+  // first 8 tiles - 64 slots per tile: 0 producer starts the tile, 1 producer issued its last k-block, 2 MMA got the
+  // accumulator, 3 MMA issued everything, 4 epilogue saw the accumulator, 5 epilogue finished its last chunk,
+  // 6 chunk manager issued the last store; 8 + kb: operands of k-block kb landed (first 40 k-blocks)
+  long long* trace = (p.trace && rank == 0) ? p.trace : nullptr;
+  auto stamp = [&](uint32_t tile_seq, int slot) {
+    if (trace && tile_seq < 8 && slot < 64) trace[tile_seq * 64 + slot] = (long long)gtimer();
+  };
+  const uint32_t a_rows = p.flat ? BM : (uint32_t)(p.tile_n * p.tile_h * p.tile_w);
+  const bool direct = op.direct != 0;
+  const bool has_res = p.res != nullptr;
+
+  auto tile_coords = [&](int tile, int& n0, int& h0, int& w0, int& c_base) {
+    const int mt = tile % op.m_tiles, nt = tile / op.m_tiles;
+    n0 = 0; h0 = 0; w0 = 0;
+    if (p.flat) {
+      w0 = mt * BM;
+    } else {
+      const int tw = mt % p.tiles_w;
+      const int t2 = mt / p.tiles_w;
+      n0 = (t2 / p.tiles_h) * p.tile_n;
+      h0 = (t2 % p.tiles_h) * p.tile_h;
+      w0 = tw * p.tile_w;
+    }
+    c_base = nt * BN;
+  };
+
+  if (warp == 0) {
+    // =================================================================== operand producer
+    if (lane == 0) {
+      prefetch_tmap(&op.tmx[0]);
+      prefetch_tmap(&op.tmw[0]);
+      const uint32_t tx_bytes = NPLANES * (a_rows * 128u + (uint32_t)L::B_PLANE);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t pit = 0;
+      for (int tile = rank; tile < n_tiles; tile += csize, ++pit) {
+        int n0, h0, w0, c_base;
+        tile_coords(tile, n0, h0, w0, c_base);
+        stamp(pit, 0);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 21);
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const int khi = tap / p.kw;
+          const int kwi = tap - khi * p.kw;
+          const uint32_t a_dst = smem_base + stage * L::STAGE;
+          const uint32_t b_dst = a_dst + NPLANES * L::A_PLANE;
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          int cw, ch, cn;
+          if (p.flat) {
+            cw = w0; ch = 0; cn = 0;
+          } else {
+            cw = w0 * p.sw + kwi - p.pad_l;
+            ch = h0 * p.sh + khi - p.pad_t;
+            cn = n0;
+          }
+          tma_load_4d(a_dst, &op.tmx[0], full_bar(stage), cb * BK, cw, ch, cn);
+          tma_load_3d(b_dst, &op.tmw[0], full_bar(stage), cb * BK, c_base, tap);
+          if (NPLANES == 2) {
+            tma_load_4d(a_dst + L::A_PLANE, &op.tmx[1], full_bar(stage), cb * BK, cw, ch, cn);
+            tma_load_3d(b_dst + L::B_PLANE, &op.tmw[1], full_bar(stage), cb * BK, c_base, tap);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        stamp(pit, 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      constexpr uint32_t idesc_wide = make_idesc<(NPLANES == 2 ? 2 * BN : BN)>();
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+        const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 22);     // epilogue drained this accumulator
+        stamp(it, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, error_flag, 23);
+          stamp(it, 8 + kb);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * L::STAGE;
+          const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
+            const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));   // NPLANES == 2: the 2*BN rows [b_hi | b_lo]
+            if (NPLANES == 2) {
+              const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
+              umma_bf16(tmem_d, a_hi, b_hi, idesc_wide, accum);   // cols [0,BN) += a_hi b_hi ; cols [BN,2BN) += a_hi b_lo
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);            // cols [0,BN) += a_lo b_hi
+            } else {
+              umma_bf16(tmem_d, a_hi, b_hi, idesc, accum);
+            }
+            accum = 1;
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(buf));
+        stamp(it, 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // =================================================================== chunk manager
+    // chunk j = (j / CH)-th tile of this CTA, 64-column block j % CH; it lives in unit j % U.
+    if (lane == 0 && !direct) {
+      const int my_tiles = rank < n_tiles ? (n_tiles - rank + csize - 1) / csize : 0;
+      const int total = my_tiles * CH;
+      if (has_res) prefetch_tmap(&op.tmr[0]);
+      prefetch_tmap(&op.tmy[0]);
+      auto coords = [&](int j, int& n0, int& h0, int& w0, int& c0) {
+        int c_base;
+        tile_coords(rank + (j / CH) * csize, n0, h0, w0, c_base);
+        c0 = c_base + (j % CH) * 64;
+      };
+      auto prepare = [&](int j) {               // make unit j % U ready for chunk j
+        const int u = j % U;
+        if (has_res) {
+          int n0, h0, w0, c0;
+          coords(j, n0, h0, w0, c0);
+          mbar_expect_tx(ready_bar(u), NPLANES * a_rows * 128u);
+          const uint32_t dst = unit_base + u * SS::UNIT;
+          tma_load_4d(dst, &op.tmr[0], ready_bar(u), c0, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+          if (NPLANES == 2) tma_load_4d(dst + BM * 128, &op.tmr[1], ready_bar(u), c0, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+        } else {
+          mbar_arrive(ready_bar(u));
+        }
+      };
+      auto retire = [&](int j) {                // ship chunk j out of its unit
+        const int u = j % U;
+        mbar_wait(done_bar(u), (uint32_t)(j / U) & 1u, error_flag, 24);
+        int n0, h0, w0, c0;
+        coords(j, n0, h0, w0, c0);
+        const uint32_t src = unit_base + u * SS::UNIT;
+        tma_store_4d(&op.tmy[0], src, c0, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+        if (NPLANES == 2) tma_store_4d(&op.tmy[1], src + BM * 128, c0, w0, p.flat ? 0 : h0, p.flat ? 0 : n0);
+        bulk_commit();
+        if (j % CH == CH - 1) stamp((uint32_t)(j / CH), 6);
+      };
+      if (U == 1) {
+        for (int j = 0; j < total; ++j) {
+          prepare(j);
+          retire(j);
+          bulk_wait_read0();
+        }
+      } else {
+        int prepared = 0;
+        for (; prepared < U - 1 && prepared < total; ++prepared) prepare(prepared);
+        for (int j = 0; j < total; ++j) {
+          retire(j);
+          if (prepared < total) {
+            // unit (j - 1) % U is next: the store of chunk j - 1 must have finished READING it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            prepare(prepared++);
+          }
+        }
+      }
+      bulk_wait_all();    // every output byte of this CTA is in global memory before the grid completes
+    }
+    __syncwarp();
+  } else {
+    // =================================================================== epilogue math (warps 3..10)
+    const int e = warp - 3;
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    const int chalf = e >> 2;                    // which 32 of the chunk's 64 columns
+    const int r = quarter * 32 + lane;           // accumulator row == tile-local pixel
+    const int sw = r & 7;
+    const bool relu = p.flags & DEFER_FLAG_RELU;
+    const float* scale_ptr = p.scale;
+    const float* shift_ptr = p.shift;
+    uint32_t it = 0, j = 0;
+    for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+      const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+      int n0, h0, w0, c_base;
+      tile_coords(tile, n0, h0, w0, c_base);
+      bool valid;
+      size_t pix;
+      row_to_pixel(p, r, n0, h0, w0, valid, pix);
+      mbar_wait(tfull_bar(buf), aphase, error_flag, 25);
+      if (threadIdx.x == 96) stamp(it, 4);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + buf * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < CH; ++c, ++j) {
+        const int col0 = c * 64 + chalf * 32;        // first accumulator column of this warp's 32
+        const int chn = c_base + col0;               // first output channel
+        const int u = (int)(j % (uint32_t)U);
+        uint8_t* stg = unit_ptr + u * SS::UNIT + r * 128;
+        if (!direct) mbar_wait(ready_bar(u), (j / (uint32_t)U) & 1u, error_flag, 26);   // residual landed / unit free
+        uint32_t v[32];
+        tmem_ld32(taddr_row + col0, v);               // warp-collective
+        if (NPLANES == 2) {
+          uint32_t v2[32];
+          tmem_ld32(taddr_row + BN + col0, v2);       // the a_hi x b_lo block of the same output columns
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(v2[q]));
+        }
+        if (c == CH - 1) {
+          // the whole accumulator is in registers (of all chunks): hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        float acc[32];
+        {
+          // per-channel scale / shift of these 32 channels (L1-resident after the first tile of a column block)
+          const float4* sp = reinterpret_cast<const float4*>(scale_ptr + chn);
+          const float4* fp = reinterpret_cast<const float4*>(shift_ptr + chn);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 a4 = scale_ptr ? __ldg(sp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 b4 = shift_ptr ? __ldg(fp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[4 * q] = fmaf(__uint_as_float(v[4 * q]), a4.x, b4.x);
+            acc[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), a4.y, b4.y);
+            acc[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a4.z, b4.z);
+            acc[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a4.w, b4.w);
+          }
+        }
+        if (has_res) {
+          if (!direct) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch16 = ((chalf * 4) + q) ^ sw;
+              const uint4 rh4 = *reinterpret_cast<const uint4*>(stg + ch16 * 16);
+              const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh4);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                acc[q * 8 + 2 * t] += __uint_as_float(hw[t] << 16);
+                acc[q * 8 + 2 * t + 1] += __uint_as_float(hw[t] & 0xffff0000u);
+              }
+              if (NPLANES == 2) {
+                const uint4 rl4 = *reinterpret_cast<const uint4*>(stg + BM * 128 + ch16 * 16);
+                const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  acc[q * 8 + 2 * t] += __uint_as_float(lw[t] << 16);
+                  acc[q * 8 + 2 * t + 1] += __uint_as_float(lw[t] & 0xffff0000u);
+                }
+              }
+            }
+          } else if (valid) {
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.cout + chn;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rh4 = *reinterpret_cast<const uint4*>(rb + q * 8);
+              const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh4);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                acc[q * 8 + 2 * t] += __uint_as_float(hw[t] << 16);
+                acc[q * 8 + 2 * t + 1] += __uint_as_float(hw[t] & 0xffff0000u);
+              }
+              if (NPLANES == 2) {
+                const uint4 rl4 = *reinterpret_cast<const uint4*>(rb + p.plane_out + q * 8);
+                const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  acc[q * 8 + 2 * t] += __uint_as_float(lw[t] << 16);
+                  acc[q * 8 + 2 * t + 1] += __uint_as_float(lw[t] & 0xffff0000u);
+                }
+              }
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[q] = fmaxf(acc[q], 0.f);
+        }
+        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.cout + chn;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 h, l;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (NPLANES == 2) {
+              split_bf16x2(acc[q * 8 + 2 * t], acc[q * 8 + 2 * t + 1], hp[t], lp[t]);
+            } else {
+              hp[t] = pack_bf16x2(acc[q * 8 + 2 * t], acc[q * 8 + 2 * t + 1]);
+            }
+          }
+          if (direct) {
+            if (valid) {
+              *reinterpret_cast<uint4*>(yp + q * 8) = h;
+              if (NPLANES == 2) *reinterpret_cast<uint4*>(yp + p.plane_out + q * 8) = l;
+            }
+          } else {
+            const int ch16 = ((chalf * 4) + q) ^ sw;
+            *reinterpret_cast<uint4*>(stg + ch16 * 16) = h;
+            if (NPLANES == 2) *reinterpret_cast<uint4*>(stg + BM * 128 + ch16 * 16) = l;
+          }
+        }
+        if (!direct) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's staging writes -> TMA engine
+          __syncwarp();
+          if (lane == 0) mbar_arrive(done_bar(u));
+        }
+        if (threadIdx.x == 96 && c == CH - 1) stamp(it, 5);
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    constexpr uint32_t ncols = 2 * ACC_COLS;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
 // weights: fp32 HWIO [tap][cin][cout]  ->  bf16 [plane][tap][cout][cin]
 __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                                int taps, int cin, int cout, int nplanes) {
@@ -1347,7 +1776,7 @@ static int env_int(const char* name, int dflt) {
 
 int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
                       int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
-                      const float* shift_dev, bool mega) {
+                      const float* shift_dev, bool mega, int stream_bn) {
   UmmaConvPlan& P = *plan;
   P = UmmaConvPlan();
   timeline_init();
@@ -1444,6 +1873,12 @@ int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin,
     P.bn = MEGA_BN;
     P.splits = 1;
     P.cluster = 0;
+  }
+  if (stream_bn > 0) {   // streaming persistent kernel: whole K loop inside the tile, N tile chosen by the caller
+    P.bn = (stream_bn == 128 && cout % 128 == 0) ? 128 : 64;
+    P.splits = 1;
+    P.cluster = 0;
+    P.stream = 1;
   }
   {
     int kb_per = (P.k_blocks + P.splits - 1) / P.splits;
@@ -1636,8 +2071,8 @@ int launch_conv_umma(const UmmaConvPlan& P, const UmmaConvLaneArgs& a, cudaStrea
 size_t umma_mega_op_bytes() { return sizeof(MegaOp); }
 
 int umma_mega_fill(void* host_dst, const UmmaConvPlan& P, const UmmaConvLaneArgs& a) {
-  if (!P.ready || P.bn != MEGA_BN || P.splits != 1) {
-    set_error("umma_mega_fill: plan is not a megakernel plan (bn %d, splits %d)", P.bn, P.splits);
+  if (!P.ready || (P.bn != MEGA_BN && !P.stream) || P.splits != 1) {
+    set_error("umma_mega_fill: plan is not a persistent-kernel plan (bn %d, splits %d)", P.bn, P.splits);
     return DEFER_ERR_STATE;
   }
   MegaOp op;
@@ -1653,7 +2088,7 @@ int umma_mega_fill(void* host_dst, const UmmaConvPlan& P, const UmmaConvLaneArgs
   op.direct = (a.direct_out || !a.has_out_maps || env_int("DEFER_EPILOGUE_DIRECT", 0)) ? 1 : 0;
   fill_kparams(P, a, &op.p);
   op.m_tiles = P.tiles_n * P.tiles_h * P.tiles_w;
-  op.n_tiles = P.cout / MEGA_BN;
+  op.n_tiles = P.cout / P.bn;
   memcpy(host_dst, &op, sizeof op);
   return DEFER_OK;
 }
@@ -1739,6 +2174,58 @@ static int launch_persist_t(const void* dev_op, int n_tiles, cudaStream_t st) {
 
 int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st) {
   return nplanes == 2 ? launch_persist_t<2>(dev_op, n_tiles, st) : launch_persist_t<1>(dev_op, n_tiles, st);
+}
+
+// ---- streaming persistent kernel: host side
+template <int NPLANES, int BN>
+static int launch_stream_t(const void* dev_op, int n_tiles, int k_blocks, cudaStream_t st) {
+  using SS = StreamSmem<NPLANES, BN>;
+  using L = SmemLayout<NPLANES, BN>;
+  constexpr int SMEM_CAP = 227 * 1024 - 256;      // opt-in limit per block (the kernel has no static shared memory)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(conv_stream_kernel<NPLANES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
+    prefer_max_smem(conv_stream_kernel<NPLANES, BN>);
+    attr_set[dev] = true;
+  }
+  static int sms = 0;
+  if (!sms) DEFER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // shared-memory split: K-heavy tiles want every byte in the operand ring (fill rate = bytes in flight / ~2 us),
+  // output-heavy tiles (a few k-blocks each) want several staging units so residual fetch, math and store overlap
+  int units = k_blocks >= env_int("DEFER_STREAM_KHEAVY", 6) ? 1 : (BN == 64 ? 4 : 3);
+  units = env_int("DEFER_STREAM_UNITS", units);
+  if (units < 1) units = 1;
+  if (units > STREAM_MAX_UNITS) units = STREAM_MAX_UNITS;
+  int stages = (SMEM_CAP - STREAM_CTL_BYTES - 1024 - units * SS::UNIT) / L::STAGE;
+  stages = env_int("DEFER_STREAM_STAGES", stages);
+  if (stages > 8) stages = 8;
+  while (stages > 1 && SS::total(stages, units) > SMEM_CAP) --stages;
+  if (stages < 1 || SS::total(stages, units) > SMEM_CAP) {
+    set_error("conv_stream: shared memory split failed (BN %d, %d units)", BN, units);
+    return DEFER_ERR_INVALID;
+  }
+  // Every CTA walks ceil(n_tiles / grid) tiles, so the launch lasts `rounds` tile-times whatever the grid is: take the
+  // SMALLEST grid that still finishes in the minimum number of rounds (448 tiles: 112 CTAs x 4 instead of 148 x 3.03)
+  // and leave the other SMs to the lanes running next to this one.
+  int grid = sms < n_tiles ? sms : n_tiles;
+  if (env_int("DEFER_STREAM_EVEN_GRID", 1)) {
+    const int rounds = (n_tiles + grid - 1) / grid;
+    grid = (n_tiles + rounds - 1) / rounds;
+  }
+  int* err = nullptr;
+  conv_stream_kernel<NPLANES, BN><<<grid, STREAM_THREADS, SS::total(stages, units), st>>>(reinterpret_cast<const MegaOp*>(dev_op),
+                                                                                         stages, units, err);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+int launch_conv_stream(int nplanes, int bn, const void* dev_op, int n_tiles, int k_blocks, cudaStream_t st) {
+  if (bn == 128) return nplanes == 2 ? launch_stream_t<2, 128>(dev_op, n_tiles, k_blocks, st) : launch_stream_t<1, 128>(dev_op, n_tiles, k_blocks, st);
+  if (bn == 64) return nplanes == 2 ? launch_stream_t<2, 64>(dev_op, n_tiles, k_blocks, st) : launch_stream_t<1, 64>(dev_op, n_tiles, k_blocks, st);
+  set_error("conv_stream: unsupported N tile %d", bn);
+  return DEFER_ERR_INVALID;
 }
 
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st) {

@@ -22,6 +22,7 @@ struct UmmaConvPlan {
   int cluster = 0;         // 1: the splits of a tile are one thread-block cluster, reduced through DSMEM
   int tma_epi = 1;         // staged epilogue (TMA residual load + TMA store) wherever one CTA owns a whole tile
   int stages = 4;          // smem ring depth (run-time: fewer stages -> more CTAs per SM)
+  int stream = 0;          // 1: plan of the streaming persistent kernel (conv_stream_kernel), N tile = bn
   size_t smem_bytes = 0;
   void* w_dev = nullptr;   // transformed weights
   const float* scale = nullptr;
@@ -48,7 +49,7 @@ bool umma_conv_supported(int fmt, int n, int h, int w, int cin, int ho, int wo, 
                          int pad_t, int pad_l);
 int umma_conv_prepare(UmmaConvPlan* plan, int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw,
                       int sh, int sw, int pad_t, int pad_l, uint32_t flags, const float* w_hwio_dev, const float* scale_dev,
-                      const float* shift_dev, bool mega = false);
+                      const float* shift_dev, bool mega = false, int stream_bn = 0);
 int umma_conv_bind(const UmmaConvPlan& plan, UmmaConvLaneArgs* args, const void* x, const void* res, void* y);
 void umma_conv_unbind(UmmaConvLaneArgs* args);
 int launch_conv_umma(const UmmaConvPlan& plan, const UmmaConvLaneArgs& args, cudaStream_t st);
@@ -60,6 +61,8 @@ size_t umma_mega_op_bytes();
 int umma_mega_fill(void* host_dst, const UmmaConvPlan& plan, const UmmaConvLaneArgs& args);   // one op descriptor
 int umma_mega_cluster_size();
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st);
+// one op on the streaming persistent kernel (deep operand ring, in-place chunked epilogue): ops with many tiles
+int launch_conv_stream(int nplanes, int bn, const void* dev_op, int n_tiles, int k_blocks, cudaStream_t st);
 // one op on a persistent grid (same kernel, grid mode): for ops with many tiles
 int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st);
 

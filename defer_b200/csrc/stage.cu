@@ -84,6 +84,7 @@ struct OpRt {
   int k_pad = 0;            // backend 4: padded patch length (multiple of 64)
   void* w_pad = nullptr;    // backend 4: zero-padded [k_pad, cout] fp32 filter matrix
   bool persist = false;     // tcgen05 conv with many tiles: persistent-grid launch (overlapped epilogue)
+  bool stream = false;      // ... on the streaming kernel (conv_stream_kernel); false = round-1 conv_mega_kernel grid mode
   int n_tiles64 = 0;
   UmmaConvPlan umma;        // valid when backend == 2
   std::string kname;
@@ -182,6 +183,10 @@ static int launch_op(defer_stage_s* s, int lane_id, int oi, cudaStream_t st) {
         DEFER_TRY(launch_stem_im2col(fmt, (const float*)x, L.im2col[oi], nb, bi.h, bi.w, bi.c, d.kh, d.kw, d.sh, d.sw, d.pad_t,
                                      d.pad_l, bo.h, bo.w, op.k_pad, st));
       if (op.backend == 2 || op.backend == 4) {
+        if (op.stream)
+          return launch_conv_stream(op.umma.nplanes, op.umma.bn, L.persist_op[oi],
+                                    op.umma.tiles_n * op.umma.tiles_h * op.umma.tiles_w * (op.umma.cout / op.umma.bn),
+                                    op.umma.k_blocks, st);
         if (op.persist) return launch_conv_persistent(op.umma.nplanes, L.persist_op[oi], op.n_tiles64, st);
         return launch_conv_umma(op.umma, L.umma[oi], st);
       }
@@ -841,29 +846,51 @@ int defer_stage_finalize(defer_stage_t s) {
       DEFER_CUDA(cudaMemset(op.w_pad, 0, (size_t)op.k_pad * bo.c * sizeof(float)));
       DEFER_CUDA(cudaMemcpy(op.w_pad, s->d_weights[d.w_kernel], kc * sizeof(float), cudaMemcpyDeviceToDevice));
     }
+    // Executor choice.  Ops of a megakernel group keep the group's 64-wide tiles.  Otherwise an op with enough output
+    // tiles runs on the streaming persistent kernel (deep operand ring, overlapped in-place epilogue); small ops keep
+    // the one-tile-per-CTA kernel (BN = 128 where C_out allows, split-K below 4 CTAs).
+    //   DEFER_STREAM=0           -> round-1 persistent kernel (conv_mega_kernel in grid mode) instead
+    //   DEFER_STREAM_MIN_TILES   -> threshold in 128 x 64 tiles (default 96)
+    //   DEFER_STREAM_BN          -> force the N tile (64 | 128); default 128 whenever C_out % 128 == 0 (tcgen05.mma has a
+    //                               ~100-cycle floor per instruction: wide N tiles halve the instruction count and the
+    //                               SM-time per output; DEFER_STREAM_BN128_TILES = minimum tile count to allow it)
+    const int stream_on = getenv("DEFER_STREAM") ? atoi(getenv("DEFER_STREAM")) : 1;
+    int stream_bn = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (stem)   // 1x1 conv over the patch matrix: "image" = output grid, channels = k_pad
         DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bo.h, bo.w, op.k_pad, bo.h, bo.w, bo.c, 1, 1, 1, 1, 0, 0,
                                     d.flags, (const float*)op.w_pad,
                                     d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
-                                    d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan));
+                                    d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan, stream_bn));
       else
       DEFER_TRY(umma_conv_prepare(&op.umma, s->cfg.fmt, s->cfg.batch, bi.h, bi.w, bi.c, bo.h, bo.w, bo.c, d.kh, d.kw, d.sh,
                                   d.sw, d.pad_t, d.pad_l, d.flags, (const float*)s->d_weights[d.w_kernel],
                                   d.w_scale >= 0 ? (const float*)s->d_weights[d.w_scale] : nullptr,
-                                  d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan));
-      op.n_tiles64 = op.umma.tiles_n * op.umma.tiles_h * op.umma.tiles_w * (bo.c / 64);
-      const char* pe = getenv("DEFER_PERSIST_MIN_TILES");
-      const int min_tiles = pe ? atoi(pe) : 192;
-      op.persist = !mega_plan ? false : (s->op_group[oi] < 0);
-      if (attempt == 0 && !mega_plan && min_tiles > 0 && op.n_tiles64 >= min_tiles) {
-        umma_conv_release(op.umma);   // many tiles: re-plan for the persistent grid (BN = 64, no split-K)
-        mega_plan = true;
-        continue;
+                                  d.w_shift >= 0 ? (const float*)s->d_weights[d.w_shift] : nullptr, mega_plan, stream_bn));
+      const int m_tiles = op.umma.tiles_n * op.umma.tiles_h * op.umma.tiles_w;
+      op.n_tiles64 = m_tiles * (bo.c / 64);
+      op.persist = (mega_plan || stream_bn > 0) && s->op_group[oi] < 0;
+      if (attempt == 0 && !mega_plan) {
+        const char* pe = getenv(stream_on ? "DEFER_STREAM_MIN_TILES" : "DEFER_PERSIST_MIN_TILES");
+        const int min_tiles = pe ? atoi(pe) : (stream_on ? 96 : 192);
+        if (min_tiles > 0 && op.n_tiles64 >= min_tiles) {
+          umma_conv_release(op.umma);   // many tiles: re-plan for a persistent grid (whole K loop per tile, no split-K)
+          if (stream_on) {
+            const char* fb = getenv("DEFER_STREAM_BN");
+            const char* mt = getenv("DEFER_STREAM_BN128_TILES");
+            const int min128 = mt ? atoi(mt) : 1;
+            stream_bn = (bo.c % 128 == 0 && m_tiles * (bo.c / 128) >= min128) ? 128 : 64;
+            if (fb && (atoi(fb) == 64 || (atoi(fb) == 128 && bo.c % 128 == 0))) stream_bn = atoi(fb);
+          } else {
+            mega_plan = true;
+          }
+          continue;
+        }
       }
       break;
     }
-    if (op.persist) op.kname = "conv_mega_kernel(grid)";
+    op.stream = op.persist && stream_bn > 0;
+    if (op.persist) op.kname = std::string(stem ? "stem_im2col+" : "") + (op.stream ? "conv_stream_kernel" : "conv_mega_kernel(grid)");
     for (int l = 0; l < s->cfg.depth; ++l) {
       Lane& L = s->lanes[l];
       // the stage output of a non-last stage is the next GPU's input slot: plain stores over NVLink

@@ -77,7 +77,7 @@ def _conv_case(torch, lib, fmt_name, backend, n, h, w, cin, cout, k, s, pad, rel
     wo = (w + 2 * pad - k) // s + 1
     res = rng.standard_normal((n, ho, wo, cout), dtype=np.float32) if residual else None
     xq = _quantise(x, fmt)
-    wq = _quantise(wk, fmt) if backend == 2 else wk
+    wq = _quantise(wk, fmt) if backend >= 2 else wk
     ref = R.conv2d(np.pad(xq.astype(np.float64), ((0, 0), (pad, pad), (pad, pad), (0, 0))), wq.astype(np.float64), None,
                    (s, s), "valid")
     ref = ref * scale.astype(np.float64) + shift.astype(np.float64)
@@ -378,3 +378,53 @@ def test_conv_tcgen05_1x1_with_bottom_right_padding(torch_cuda, fmt_name):
     y = _decode(torch, lib, yd, fmt, ref.shape)
     assert R.rel_err(y, ref) <= TOL[fmt_name]
     assert np.allclose(y[:, h:, :, :], shift, atol=1e-2)      # the padded rows / columns see only the shift
+
+
+STREAM_SHAPES = [
+    # n, h, w, cin, cout, k, s, pad
+    (8, 56, 56, 64, 256, 1, 1, 0),      # flat, one k-block per tile, 4 / 2 column blocks
+    (4, 56, 56, 64, 64, 3, 1, 1),       # 3x3, N = 64 only, 112-row tiles
+    (8, 28, 28, 256, 512, 1, 2, 0),     # stride 2 through TMA element strides
+    (3, 14, 14, 256, 256, 3, 1, 1),     # 98-row tiles, K-heavy (36 k-blocks)
+    (16, 7, 7, 512, 512, 3, 1, 1),      # two images per tile, 72 k-blocks
+    (5, 14, 14, 1024, 256, 1, 1, 0),    # flat, ragged last M tile (980 rows), 16 k-blocks
+    (2, 28, 28, 128, 128, 3, 1, 1),
+    (1, 56, 56, 256, 64, 1, 1, 0),
+    (9, 7, 7, 2048, 512, 1, 1, 0),      # 441 rows: 4 tiles, 32 k-blocks
+]
+
+
+@pytest.mark.parametrize("fmt_name", ["bf16x2", "bf16"])
+@pytest.mark.parametrize("shape", STREAM_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_stream_kernel(torch_cuda, fmt_name, shape):
+    """conv_stream_kernel (deep operand ring, in-place chunked epilogue): 64- and 128-wide N tiles, staged (TMA) and
+    per-thread (peer-capable) epilogues, with and without residual / ReLU - against the fp64 oracle, and bit-identical
+    across tile widths and epilogue kinds (same K order per output)."""
+    torch, lib = torch_cuda
+    n, h, w, cin, cout, k, s, pad = shape
+    i = STREAM_SHAPES.index(shape)
+    outs = {}
+    for backend in (4, 5, 6, 7):
+        for residual in (False, True):
+            err, y, _ = _conv_case(torch, lib, fmt_name, backend, n, h, w, cin, cout, k, s, pad, relu=(i % 2 == 0),
+                                   residual=residual, seed=100 + i)
+            assert err <= TOL[fmt_name], (fmt_name, shape, backend, residual, err)
+            outs[(backend, residual)] = y
+    for residual in (False, True):
+        for backend in (5, 6, 7):
+            assert np.array_equal(outs[(backend, residual)], outs[(4, residual)]), (shape, backend, residual)
+
+
+@pytest.mark.parametrize("units,stages", [(1, 0), (2, 0), (3, 0), (4, 2), (2, 1)])
+def test_conv_stream_kernel_smem_splits(torch_cuda, units, stages, monkeypatch):
+    """Every (ring depth, staging units) split the host may pick must give the same bits."""
+    torch, lib = torch_cuda
+    shapes = [(4, 56, 56, 64, 256, 1, 1, 0), (3, 14, 14, 256, 256, 3, 1, 1)]
+    ref = [_conv_case(torch, lib, "bf16x2", 5, *sh, relu=True, residual=True, seed=7 + j)[1] for j, sh in enumerate(shapes)]
+    monkeypatch.setenv("DEFER_STREAM_UNITS", str(units))
+    if stages:
+        monkeypatch.setenv("DEFER_STREAM_STAGES", str(stages))
+    for j, sh in enumerate(shapes):
+        for backend in (4, 5):
+            err, y, _ = _conv_case(torch, lib, "bf16x2", backend, *sh, relu=True, residual=True, seed=7 + j)
+            assert err <= TOL["bf16x2"] and np.array_equal(y, ref[j]), (units, stages, sh, backend)

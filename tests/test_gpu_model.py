@@ -286,3 +286,23 @@ def test_defer_coalesced_items_fifo_and_parity(resnet50, x224, coalesce):
         defer.close()
         t.join(timeout=30)
     assert not t.is_alive()
+
+
+def test_batch8_stream_kernel_vs_oracle_and_round1_executor(resnet50, monkeypatch):
+    """A coalesced microbatch of 8 different images runs most convs on conv_stream_kernel: parity with the oracle per
+    image, and agreement with the round-1 persistent executor (DEFER_STREAM=0) to summation-order noise."""
+    x = applications.synthetic_input(8, seed=17)
+    x *= np.linspace(0.7, 1.3, 8, dtype=np.float32).reshape(8, 1, 1, 1)
+    outs = {}
+    for stream in ("1", "0"):
+        monkeypatch.setenv("DEFER_STREAM", stream)
+        r = StageRunner.from_model(resnet50, device=0, dtype="float32", max_batch=8, depth=1)
+        try:
+            outs[stream] = r.predict(x)
+            assert ("conv_stream_kernel" in r.describe()) == (stream == "1")
+        finally:
+            r.close()
+    ref = _oracle(resnet50, x)
+    for i in range(8):
+        assert _rel(outs["1"][i], ref[i]) <= 1e-3, i
+    assert _rel(outs["1"], outs["0"]) <= 1e-4
