@@ -828,6 +828,9 @@ struct alignas(128) MegaOp {
   int m_tiles, n_tiles;     // tiles of this op: m fastest
   int direct;               // 1: per-thread st.global / ld.global epilogue (output in a peer GPU's slot)
   int pad_[1];
+  // fused stem (conv_stem_kernel): the fp32 NHWC image the patch rows are built from, and the real conv geometry
+  const float* stem_x;
+  int stem_h, stem_w, stem_cin, stem_kh, stem_kw, stem_sh, stem_sw, stem_pad_t, stem_pad_l, stem_K;
 };
 
 constexpr int MEGA_BN = 64;
@@ -1642,6 +1645,355 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
   }
 }
 
+// ==============================================================================================
+// Fused stem: [ZeroPadding2D +] Conv2D with a few input channels (RGB, fp32 image) + bias/BN + ReLU on the tensor cores
+// WITHOUT a patch matrix in global memory (round 1 wrote and re-read 9.6 MB per image for a 0.6 MB input).
+//
+// GEMM view: M = output pixels (flat, 128 per tile), N = 64, K = kh*kw*cin padded to a multiple of 64 (147 -> 192).
+// In NHWC a patch is kh runs of kw*cin CONTIGUOUS floats, so k -> (kernel row a, offset jj) and one range check on the
+// flat column index covers the left / right zero padding.  Per tile:
+//   * warp 0 (producer) bulk-copies the few fp32 input rows the tile's pixels need into shared memory (one
+//     cp.async.bulk, double-buffered) and TMA-loads the weight k-blocks into the operand ring;
+//   * warps 7-14 (builders, two threads per tile row) turn those rows into the A operand: K-major SWIZZLE_128B rows of bf16 hi / lo planes,
+//     written with st.shared straight into the ring stage, then fence.proxy.async + arrive on the stage's full barrier;
+//   * warp 1 issues the same two-instruction fp32-parity MMAs as conv_stream_kernel into one of two TMEM accumulators;
+//   * warps 3-6 run the epilogue (scale/shift, ReLU, hi/lo split into a swizzled staging unit), warp 2 TMA-stores it.
+// Requirements (host checks them, otherwise the im2col + GEMM pair is used): C_out == 64, (ho*wo) % 128 == 0 (a tile
+// never straddles two images), output stored locally (no peer slot), no residual.
+// ==============================================================================================
+constexpr int STEM_EPI_WARPS = 4;
+constexpr int STEM_BUILD_WARPS = 8;       // two threads per tile row: each builds 4 of the 8 16-byte chunks of a k-block row
+constexpr int STEM_THREADS = 96 + 32 * (STEM_EPI_WARPS + STEM_BUILD_WARPS);   // 480
+constexpr int STEM_CTL_BYTES = 512;
+
+template <int NPLANES>
+struct StemSmem {
+  using L = SmemLayout<NPLANES, 64>;
+  static constexpr int UNIT = NPLANES * BM * 128;
+  __host__ __device__ static constexpr int unit_off(int stages) { return stages * L::STAGE; }
+  __host__ __device__ static constexpr int in_off(int stages) { return stages * L::STAGE + 2 * UNIT; }
+  __host__ __device__ static constexpr int ctl_off(int stages, int in_bytes) { return in_off(stages) + 2 * in_bytes; }
+  __host__ __device__ static constexpr int total(int stages, int in_bytes) { return ctl_off(stages, in_bytes) + STEM_CTL_BYTES + 1024; }
+};
+
+template <int NPLANES>
+__global__ void __launch_bounds__(STEM_THREADS, 1)
+conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int max_rows, int* error_flag) {
+  constexpr int BN = 64;
+  using L = SmemLayout<NPLANES, BN>;
+  using SS = StemSmem<NPLANES>;
+  constexpr int ACC_COLS = NPLANES == 2 ? 2 * BN : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int STAGES = stages;
+  const uint32_t bar_base = smem_base + SS::ctl_off(STAGES, in_bytes);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                      // [0, 8): 1 producer + 4 builder warps
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };               // [8, 16)
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  auto ready_bar = [&](int u) { return bar_base + 8u * (20 + u); };              // staging unit may be written
+  auto done_bar = [&](int u) { return bar_base + 8u * (22 + u); };               // staging unit holds a finished tile
+  auto in_full_bar = [&](int b) { return bar_base + 8u * (24 + b); };            // input rows landed
+  auto in_empty_bar = [&](int b) { return bar_base + 8u * (26 + b); };           // builders are done with them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, in_bytes) + 8 * 28);
+  const uint32_t unit_base = smem_base + SS::unit_off(STAGES);
+  uint8_t* unit_ptr = smem + SS::unit_off(STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const MegaOp& op = *opp;
+  const KParams& p = op.p;
+  const int n_tiles = op.m_tiles;                  // one 64-wide column block
+  const int rank = (int)blockIdx.x, csize = (int)gridDim.x;
+  const int H = op.stem_h, W = op.stem_w, CIN = op.stem_cin;
+  const int row_len = W * CIN;                     // floats per input row
+  const int run = op.stem_kw * CIN;                // contiguous floats per kernel row of a patch
+  const int hw_out = p.ho * p.wo;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + STEM_BUILD_WARPS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), STEM_EPI_WARPS);
+      mbar_init(ready_bar(b), 1);
+      mbar_init(done_bar(b), STEM_EPI_WARPS);
+      mbar_init(in_full_bar(b), 1);
+      mbar_init(in_empty_bar(b), STEM_BUILD_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    constexpr uint32_t ncols = 2 * ACC_COLS;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // input rows a tile needs: pixels [p0, p0 + 128) of image nb cover output rows oh0..oh1
+  auto tile_rows = [&](int tile, int& nb, int& oh0, int& ih_lo, int& n_rows) {
+    const int p0 = tile * BM;
+    nb = p0 / hw_out;
+    const int q0 = p0 - nb * hw_out;
+    oh0 = q0 / p.wo;
+    const int oh1 = (q0 + BM - 1) / p.wo;
+    int lo = oh0 * op.stem_sh - op.stem_pad_t;
+    int hi = oh1 * op.stem_sh - op.stem_pad_t + op.stem_kh - 1;
+    if (lo < 0) lo = 0;
+    if (hi > H - 1) hi = H - 1;
+    ih_lo = lo;
+    n_rows = hi - lo + 1;
+  };
+
+  if (warp == 0) {
+    // =================================================================== producer: input rows + weight k-blocks
+    if (lane == 0) {
+      prefetch_tmap(&op.tmw[0]);
+      const uint32_t b_bytes = NPLANES * (uint32_t)L::B_PLANE;
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+        const uint32_t ib = it & 1, iph = (it >> 1) & 1;
+        int nb, oh0, ih_lo, n_rows;
+        tile_rows(tile, nb, oh0, ih_lo, n_rows);
+        mbar_wait(in_empty_bar(ib), iph ^ 1, error_flag, 31);
+        const uint32_t bytes = (uint32_t)n_rows * (uint32_t)row_len * 4u;
+        mbar_expect_tx(in_full_bar(ib), bytes);
+        const float* src = op.stem_x + ((size_t)nb * H + ih_lo) * row_len;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_base + SS::in_off(STAGES) + ib * in_bytes), "l"(src), "r"(bytes), "r"(in_full_bar(ib)) : "memory");
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 32);
+          const uint32_t b_dst = smem_base + stage * L::STAGE + NPLANES * L::A_PLANE;
+          mbar_expect_tx(full_bar(stage), b_bytes);
+          tma_load_3d(b_dst, &op.tmw[0], full_bar(stage), kb * BK, 0, 0);
+          if (NPLANES == 2) tma_load_3d(b_dst + L::B_PLANE, &op.tmw[1], full_bar(stage), kb * BK, 0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      constexpr uint32_t idesc_wide = make_idesc<(NPLANES == 2 ? 2 * BN : BN)>();
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+        const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 33);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, error_flag, 34);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * L::STAGE;
+          const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_hi = make_sw128_desc(a_addr + k * (UMMA_K * 2));
+            const uint64_t b_hi = make_sw128_desc(b_addr + k * (UMMA_K * 2));
+            if (NPLANES == 2) {
+              const uint64_t a_lo = make_sw128_desc(a_addr + L::A_PLANE + k * (UMMA_K * 2));
+              umma_bf16(tmem_d, a_hi, b_hi, idesc_wide, accum);
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+            } else {
+              umma_bf16(tmem_d, a_hi, b_hi, idesc, accum);
+            }
+            accum = 1;
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // =================================================================== store manager (two staging units)
+    if (lane == 0) {
+      prefetch_tmap(&op.tmy[0]);
+      uint32_t it = 0;
+      mbar_arrive(ready_bar(0));
+      mbar_arrive(ready_bar(1));
+      for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+        const uint32_t u = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(done_bar(u), ph, error_flag, 35);
+        const uint32_t src = unit_base + u * SS::UNIT;
+        tma_store_4d(&op.tmy[0], src, 0, tile * BM, 0, 0);
+        if (NPLANES == 2) tma_store_4d(&op.tmy[1], src + BM * 128, 0, tile * BM, 0, 0);
+        bulk_commit();
+        if (tile + csize < n_tiles) {
+          // unit u ^ 1 (tile it + 1) is already released; unit u is needed again by tile it + 2: its store (this one)
+          // must have finished reading - checked one iteration later, when only the newest group may still be pending
+          if (it >= 1) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(ready_bar(u ^ 1));
+          }
+        }
+      }
+      bulk_wait_all();
+    }
+    __syncwarp();
+  } else if (warp < 3 + STEM_EPI_WARPS) {
+    // =================================================================== epilogue (warps 3..6): 64 columns per thread row
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int sw = r & 7;
+    const bool relu = p.flags & DEFER_FLAG_RELU;
+    const float* scale_ptr = p.scale;
+    const float* shift_ptr = p.shift;
+    uint32_t it = 0;
+    for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+      const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(buf), aphase, error_flag, 36);
+      tc_fence_after();
+      mbar_wait(ready_bar(buf), aphase, error_flag, 37);       // staging unit `buf` is free (its previous store has read it)
+      const uint32_t taddr_row = tmem_base + buf * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      uint8_t* stg = unit_ptr + buf * SS::UNIT + r * 128;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int col0 = half * 32;
+        uint32_t v[32];
+        tmem_ld32(taddr_row + col0, v);
+        if (NPLANES == 2) {
+          uint32_t v2[32];
+          tmem_ld32(taddr_row + BN + col0, v2);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(v2[q]));
+        }
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        float acc[32];
+        {
+          const float4* sp = reinterpret_cast<const float4*>(scale_ptr + col0);
+          const float4* fp = reinterpret_cast<const float4*>(shift_ptr + col0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 a4 = scale_ptr ? __ldg(sp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 b4 = shift_ptr ? __ldg(fp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[4 * q] = fmaf(__uint_as_float(v[4 * q]), a4.x, b4.x);
+            acc[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), a4.y, b4.y);
+            acc[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a4.z, b4.z);
+            acc[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a4.w, b4.w);
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[q] = fmaxf(acc[q], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 h, l;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (NPLANES == 2) split_bf16x2(acc[q * 8 + 2 * t], acc[q * 8 + 2 * t + 1], hp[t], lp[t]);
+            else hp[t] = pack_bf16x2(acc[q * 8 + 2 * t], acc[q * 8 + 2 * t + 1]);
+          }
+          const int ch16 = ((half * 4) + q) ^ sw;
+          *reinterpret_cast<uint4*>(stg + ch16 * 16) = h;
+          if (NPLANES == 2) *reinterpret_cast<uint4*>(stg + BM * 128 + ch16 * 16) = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done_bar(buf));
+    }
+  } else {
+    // =================================================================== A builders (warps 7..14): two threads per tile row
+    const int bt = threadIdx.x - 32 * (3 + STEM_EPI_WARPS);          // 0..255
+    const int r = bt & (BM - 1);
+    const int g0 = (bt >> 7) * 4;                                    // this thread's 4 chunks (32 k) of every k-block
+    const int sw = r & 7;
+    int stage = 0;
+    uint32_t phase = 0, it = 0;
+    for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
+      const uint32_t ib = it & 1, iph = (it >> 1) & 1;
+      int nb, oh0, ih_lo, n_rows;
+      tile_rows(tile, nb, oh0, ih_lo, n_rows);
+      const int q = tile * BM + r - nb * hw_out;       // pixel index inside the image
+      const int oh = q / p.wo, ow = q - oh * p.wo;
+      const int ih0 = oh * op.stem_sh - op.stem_pad_t;                 // input row of kernel row 0
+      const int col0 = (ow * op.stem_sw - op.stem_pad_l) * CIN;        // flat column of the patch's first element
+      // kernel rows whose input row exists (zero padding above / below, and a >= kh for the K padding): one bit each
+      uint32_t rowmask = 0;
+      for (int a = 0; a < op.stem_kh; ++a) {
+        const int ih = ih0 + a;
+        if (ih >= ih_lo && ih < ih_lo + n_rows) rowmask |= 1u << a;
+      }
+      const bool colfast = col0 >= 0 && col0 + run <= row_len;         // no left / right padding inside this patch
+      const float* rows = reinterpret_cast<const float*>(smem + SS::in_off(STAGES) + ib * in_bytes) + (ih0 - ih_lo) * row_len + col0;
+      mbar_wait(in_full_bar(ib), iph, error_flag, 38);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 39);
+        uint8_t* a_row = smem + stage * L::STAGE + r * 128;
+        int k = kb * BK + g0 * 8;
+        int a = k / run, jj = k - a * run;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float val = 0.f;
+            if ((rowmask >> a) & 1u) {
+              if (colfast || (col0 + jj >= 0 && col0 + jj < row_len)) val = rows[a * row_len + jj];
+            }
+            v[j] = val;
+            if (++jj == run) { jj = 0; ++a; }
+          }
+          const int ch16 = (g0 + g) ^ sw;
+          if (NPLANES == 2) {
+            uint4 hv, lv;
+            split_bf16x2(v[0], v[1], hv.x, lv.x);
+            split_bf16x2(v[2], v[3], hv.y, lv.y);
+            split_bf16x2(v[4], v[5], hv.z, lv.z);
+            split_bf16x2(v[6], v[7], hv.w, lv.w);
+            *reinterpret_cast<uint4*>(a_row + ch16 * 16) = hv;
+            *reinterpret_cast<uint4*>(a_row + L::A_PLANE + ch16 * 16) = lv;
+          } else {
+            uint4 hv;
+            hv.x = pack_bf16x2(v[0], v[1]);
+            hv.y = pack_bf16x2(v[2], v[3]);
+            hv.z = pack_bf16x2(v[4], v[5]);
+            hv.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a_row + ch16 * 16) = hv;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty_bar(ib));
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    constexpr uint32_t ncols = 2 * ACC_COLS;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
 // weights: fp32 HWIO [tap][cin][cout]  ->  bf16 [plane][tap][cout][cin]
 __global__ void __launch_bounds__(256) weight_transform_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                                int taps, int cin, int cout, int nplanes) {
@@ -2226,6 +2578,68 @@ int launch_conv_stream(int nplanes, int bn, const void* dev_op, int n_tiles, int
   if (bn == 64) return nplanes == 2 ? launch_stream_t<2, 64>(dev_op, n_tiles, k_blocks, st) : launch_stream_t<1, 64>(dev_op, n_tiles, k_blocks, st);
   set_error("conv_stream: unsupported N tile %d", bn);
   return DEFER_ERR_INVALID;
+}
+
+// ---- fused stem: host side
+int umma_stem_in_bytes(int wo, int w, int cin, int kh, int sh) {
+  const int span = (BM + wo - 2) / wo;            // a 128-pixel tile touches at most span + 1 output rows
+  const int rows = span * sh + kh;
+  return ((rows * w * cin * 4) + 1023) / 1024 * 1024;
+}
+
+bool umma_stem_fusable(int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int sh, uint32_t flags) {
+  if (fmt != FMT_BF16X2 && fmt != FMT_BF16) return false;
+  if (cout != 64 || (flags & DEFER_FLAG_RESIDUAL)) return false;
+  if (((long long)ho * wo) % BM != 0) return false;              // a tile never straddles two images
+  if ((w * cin * 4) % 16 != 0) return false;                      // bulk copies move whole 16-byte units
+  using SS2 = StemSmem<2>;
+  const int in_bytes = umma_stem_in_bytes(wo, w, cin, kh, sh);
+  (void)n; (void)h;
+  return SS2::total(2, in_bytes) <= 227 * 1024 - 256;
+}
+
+void umma_mega_set_stem(void* host_op, const float* x, int h, int w, int cin, int kh, int kw, int sh, int sw, int pad_t, int pad_l) {
+  MegaOp* op = reinterpret_cast<MegaOp*>(host_op);
+  op->stem_x = x;
+  op->stem_h = h; op->stem_w = w; op->stem_cin = cin;
+  op->stem_kh = kh; op->stem_kw = kw; op->stem_sh = sh; op->stem_sw = sw;
+  op->stem_pad_t = pad_t; op->stem_pad_l = pad_l;
+  op->stem_K = kh * kw * cin;
+}
+
+template <int NPLANES>
+static int launch_stem_t(const void* dev_op, int n_tiles, int in_bytes, cudaStream_t st) {
+  using SS = StemSmem<NPLANES>;
+  using L = SmemLayout<NPLANES, 64>;
+  constexpr int SMEM_CAP = 227 * 1024 - 256;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  DEFER_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    DEFER_CUDA(cudaFuncSetAttribute(conv_stem_kernel<NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
+    prefer_max_smem(conv_stem_kernel<NPLANES>);
+    attr_set[dev] = true;
+  }
+  static int sms = 0;
+  if (!sms) DEFER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int stages = (SMEM_CAP - STEM_CTL_BYTES - 1024 - 2 * SS::UNIT - 2 * in_bytes) / L::STAGE;
+  if (stages > 8) stages = 8;
+  if (stages < 2) {
+    set_error("conv_stem: shared memory split failed (%d input bytes)", in_bytes);
+    return DEFER_ERR_INVALID;
+  }
+  int grid = sms < n_tiles ? sms : n_tiles;
+  const int rounds = (n_tiles + grid - 1) / grid;
+  grid = (n_tiles + rounds - 1) / rounds;
+  int* err = nullptr;
+  conv_stem_kernel<NPLANES><<<grid, STEM_THREADS, SS::total(stages, in_bytes), st>>>(reinterpret_cast<const MegaOp*>(dev_op), stages,
+                                                                                   in_bytes, 0, err);
+  DEFER_CUDA(cudaGetLastError());
+  return DEFER_OK;
+}
+
+int launch_conv_stem(int nplanes, const void* dev_op, int n_tiles, int in_bytes, cudaStream_t st) {
+  return nplanes == 2 ? launch_stem_t<2>(dev_op, n_tiles, in_bytes, st) : launch_stem_t<1>(dev_op, n_tiles, in_bytes, st);
 }
 
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st) {

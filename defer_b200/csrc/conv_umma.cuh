@@ -63,6 +63,11 @@ int umma_mega_cluster_size();
 int launch_conv_mega(int nplanes, const void* dev_ops, int n_ops, cudaStream_t st);
 // one op on the streaming persistent kernel (deep operand ring, in-place chunked epilogue): ops with many tiles
 int launch_conv_stream(int nplanes, int bn, const void* dev_op, int n_tiles, int k_blocks, cudaStream_t st);
+// fused stem (conv_stem_kernel): conv over a few-channel fp32 image with the im2col done inside the tcgen05 kernel
+bool umma_stem_fusable(int fmt, int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int sh, uint32_t flags);
+int umma_stem_in_bytes(int wo, int w, int cin, int kh, int sh);
+void umma_mega_set_stem(void* host_op, const float* x, int h, int w, int cin, int kh, int kw, int sh, int sw, int pad_t, int pad_l);
+int launch_conv_stem(int nplanes, const void* dev_op, int n_tiles, int in_bytes, cudaStream_t st);
 // one op on a persistent grid (same kernel, grid mode): for ops with many tiles
 int launch_conv_persistent(int nplanes, const void* dev_op, int n_tiles, cudaStream_t st);
 

@@ -84,6 +84,8 @@ struct OpRt {
   int k_pad = 0;            // backend 4: padded patch length (multiple of 64)
   void* w_pad = nullptr;    // backend 4: zero-padded [k_pad, cout] fp32 filter matrix
   bool persist = false;     // tcgen05 conv with many tiles: persistent-grid launch (overlapped epilogue)
+  bool stem_fused = false;  // backend 4 without a patch matrix: conv_stem_kernel builds the A operand from the fp32 image
+  int stem_in_bytes = 0;
   bool stream = false;      // ... on the streaming kernel (conv_stream_kernel); false = round-1 conv_mega_kernel grid mode
   int n_tiles64 = 0;
   UmmaConvPlan umma;        // valid when backend == 2
@@ -105,7 +107,18 @@ struct Lane {
   std::vector<void*> persist_op;       // per op: device op descriptor for the persistent-grid launch
   std::vector<void*> im2col;           // per op (backend 4): patch matrix scratch
   bool timed = false;
+  void* peer_out = nullptr;   // HOP_COPY: this lane's input slot on the consumer GPU (destination of the hop copy)
 };
+
+// How a non-last stage's output reaches the next GPU's input slot (DEFER_HOP, read when the stage is created):
+//   HOP_COPY   (default) the last op writes a LOCAL buffer with its normal (TMA-store) epilogue; then the lane waits for the
+//              slot's free flag and a cudaMemcpyAsync (copy engine, captured in the lane graph) ships it over NVLink in
+//              full-line bursts - the north star's cudaMemcpyPeerAsync hop.  Compute never blocks on back-pressure and no
+//              SM spends time on 16-byte peer stores (measured round 2: the per-thread peer-store epilogue capped every
+//              multi-GPU pipeline at ~30 k inf/s, 51 MB per 16-image microbatch out of stage 0 at ~150 GB/s).
+//   HOP_TMA    the last op's TMA store targets the peer slot directly (tensor map encoded on the mapped peer address).
+//   HOP_DIRECT round-1 behaviour: per-thread st.global of the epilogue into the peer slot.
+enum HopMode { HOP_COPY = 0, HOP_TMA = 1, HOP_DIRECT = 2 };
 
 struct Mark {                 // steady-state timing: an event recorded right behind one chosen microbatch
   cudaEvent_t ev = nullptr;
@@ -140,6 +153,7 @@ struct defer_stage_s {
   size_t max_dense_partial = 0;
   cudaEvent_t job_t0 = nullptr, job_t1 = nullptr;
   Mark marks[2];
+  int hop = HOP_COPY;
   // megakernel groups: runs of consecutive tcgen05 convs executed by one cluster launch per lane
   struct MegaGroup {
     int first = 0, last = 0;
@@ -179,6 +193,9 @@ static int launch_op(defer_stage_s* s, int lane_id, int oi, cudaStream_t st) {
   auto wptr = [&](int id) -> const float* { return id >= 0 ? (const float*)s->d_weights[id] : nullptr; };
   switch (d.kind) {
     case DEFER_OP_CONV: {
+      if (op.backend == 4 && op.stem_fused)
+        return launch_conv_stem(op.umma.nplanes, L.persist_op[oi], op.umma.tiles_n * op.umma.tiles_h * op.umma.tiles_w,
+                                op.stem_in_bytes, st);
       if (op.backend == 4)
         DEFER_TRY(launch_stem_im2col(fmt, (const float*)x, L.im2col[oi], nb, bi.h, bi.w, bi.c, d.kh, d.kw, d.sh, d.sw, d.pad_t,
                                      d.pad_l, bo.h, bo.w, op.k_pad, st));
@@ -244,7 +261,7 @@ static int enqueue_lane(defer_stage_s* s, int lane_id, cudaStream_t st) {
     const int g = s->op_group.empty() ? -1 : s->op_group[oi];
     if (g >= 0 && oi != s->groups[g].first) continue;          // executed by its group's launch
     const int span_last = g >= 0 ? s->groups[g].last : oi;
-    if (s->has_cons && s->output_writer >= oi && s->output_writer <= span_last)
+    if (s->has_cons && s->hop != HOP_COPY && s->output_writer >= oi && s->output_writer <= span_last)
       DEFER_TRY(launch_wait_flag(s->free_flag(lane_id), s->counter(CTR_WAIT_FREE, lane_id), 1, s->status_ptr(),
                                  s->timeout_ns, st));
     if (g >= 0) {
@@ -256,6 +273,13 @@ static int enqueue_lane(defer_stage_s* s, int lane_id, cudaStream_t st) {
       uint32_t* remote = reinterpret_cast<uint32_t*>(s->prod_arena + OFF_FREE + lane_id * FLAG_STRIDE);
       DEFER_TRY(launch_signal_flag(remote, s->counter(CTR_SIG_FREE, lane_id), s->status_ptr(), st));
     }
+  }
+  if (s->has_cons && s->hop == HOP_COPY) {
+    // the hop: back-pressure (slot free?) is only checked now, after all compute of this microbatch; the payload goes
+    // out through the copy engine as one device-to-device copy over NVLink
+    Lane& L = s->lanes[lane_id];
+    DEFER_TRY(launch_wait_flag(s->free_flag(lane_id), s->counter(CTR_WAIT_FREE, lane_id), 1, s->status_ptr(), s->timeout_ns, st));
+    DEFER_CUDA(cudaMemcpyAsync(L.peer_out, L.buf[s->cfg.output_buf], s->bufs[s->cfg.output_buf].bytes, cudaMemcpyDeviceToDevice, st));
   }
   if (s->has_cons) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(s->cons_arena + OFF_READY + lane_id * FLAG_STRIDE);
@@ -359,6 +383,12 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
 
   defer_stage_s* s = new defer_stage_s();
   s->cfg = *cfg;
+  {
+    const char* hm = getenv("DEFER_HOP");
+    s->hop = HOP_COPY;
+    if (hm && !strcmp(hm, "tma")) s->hop = HOP_TMA;
+    else if (hm && !strcmp(hm, "direct")) s->hop = HOP_DIRECT;
+  }
   if (cfg->wait_timeout_ms > 0) s->timeout_ns = (unsigned long long)cfg->wait_timeout_ms * 1000000ull;
   int rc = DEFER_OK;
   auto fail = [&](int code) {
@@ -572,7 +602,7 @@ int defer_stage_create(const defer_stage_config* cfg, const defer_buf_desc* bufs
     L.buf[cfg->input_buf] = s->arena + CTRL_BYTES + s->slot_stride * l;
     for (int b = 0; b < n_bufs; ++b) {
       if (b == cfg->input_buf) continue;
-      if (b == cfg->output_buf && !cfg->is_last) continue;  // bound to the consumer's slot at link time
+      if (b == cfg->output_buf && !cfg->is_last && s->hop != HOP_COPY) continue;  // bound to the consumer's slot at link time
       void* p = nullptr;
       size_t bytes = (s->bufs[b].bytes + 255) / 256 * 256;
       if (cudaMalloc(&p, bytes) != cudaSuccess) {
@@ -718,8 +748,11 @@ static int apply_token(defer_stage_t s, int role, const LinkToken* t, uint8_t* m
     s->cons_is_ipc = is_ipc;
     s->cons_off_slots = t->off_slots;
     s->cons_slot_stride = t->slot_stride;
-    for (int l = 0; l < s->cfg.depth; ++l)
-      s->lanes[l].buf[s->cfg.output_buf] = mapped + t->off_slots + t->slot_stride * l;
+    for (int l = 0; l < s->cfg.depth; ++l) {
+      void* slot = mapped + t->off_slots + t->slot_stride * l;
+      if (s->hop == HOP_COPY) s->lanes[l].peer_out = slot;          // output stays local, a copy node ships it
+      else s->lanes[l].buf[s->cfg.output_buf] = slot;               // the last op writes the peer slot itself
+    }
     s->has_cons = true;
   } else {
     DEFER_CHECK(!s->cfg.is_first, "link: the first stage has no producer");
@@ -891,19 +924,31 @@ int defer_stage_finalize(defer_stage_t s) {
     }
     op.stream = op.persist && stream_bn > 0;
     if (op.persist) op.kname = std::string(stem ? "stem_im2col+" : "") + (op.stream ? "conv_stream_kernel" : "conv_mega_kernel(grid)");
+    // fused stem: no patch matrix at all when the tile geometry allows it and the output stays on this GPU
+    {
+      static const int fuse = getenv("DEFER_STEM_FUSED") ? atoi(getenv("DEFER_STEM_FUSED")) : 1;
+      const bool out_local = s->hop == HOP_COPY || !((d.out == s->cfg.output_buf) && !s->cfg.is_last);
+      op.stem_fused = stem && fuse && op.stream && op.umma.bn == 64 && op.umma.flat && out_local &&
+                      umma_stem_fusable(s->cfg.fmt, s->cfg.batch, bi.h, bi.w, bi.c, bo.h, bo.w, bo.c, d.kh, d.sh, d.flags);
+      if (op.stem_fused) {
+        op.stem_in_bytes = umma_stem_in_bytes(bo.w, bi.w, bi.c, d.kh, d.sh);
+        op.kname = "conv_stem_kernel";
+        op.n_kernels = 1;
+      }
+    }
     for (int l = 0; l < s->cfg.depth; ++l) {
       Lane& L = s->lanes[l];
       // the stage output of a non-last stage is the next GPU's input slot: plain stores over NVLink
-      L.umma[oi].direct_out = (d.out == s->cfg.output_buf) && !s->cfg.is_last;
+      L.umma[oi].direct_out = (d.out == s->cfg.output_buf) && !s->cfg.is_last && s->hop == HOP_DIRECT;
       const void* conv_in = L.buf[d.in0];
       if (stem) {
         if (L.im2col.size() < s->ops.size()) L.im2col.resize(s->ops.size(), nullptr);
-        if (!L.im2col[oi]) {
+        if (!L.im2col[oi] && !op.stem_fused) {
           const size_t bytes = (size_t)s->cfg.batch * bo.h * bo.w * op.k_pad * fmt_bytes_per_elem(s->cfg.fmt);
           DEFER_CUDA(cudaMalloc(&L.im2col[oi], bytes));
           s->workspace.push_back(L.im2col[oi]);
         }
-        conv_in = L.im2col[oi];
+        conv_in = op.stem_fused ? L.buf[d.out] : L.im2col[oi];   // fused: the A tensor map is never used (any valid pointer)
       }
       DEFER_TRY(umma_conv_bind(op.umma, &L.umma[oi], conv_in,
                                (d.flags & DEFER_FLAG_RESIDUAL) ? L.buf[d.in1] : nullptr, L.buf[d.out]));
@@ -918,6 +963,11 @@ int defer_stage_finalize(defer_stage_t s) {
       Lane& L = s->lanes[l];
       L.persist_op.resize(s->ops.size(), nullptr);
       DEFER_TRY(umma_mega_fill(host.data(), op.umma, L.umma[oi]));
+      if (op.stem_fused) {
+        const defer_op_desc& d = op.d;
+        const Buf& bi = s->bufs[d.in0];
+        umma_mega_set_stem(host.data(), (const float*)L.buf[d.in0], bi.h, bi.w, bi.c, d.kh, d.kw, d.sh, d.sw, d.pad_t, d.pad_l);
+      }
       DEFER_CUDA(cudaMalloc(&L.persist_op[oi], ob));
       s->workspace.push_back(L.persist_op[oi]);
       DEFER_CUDA(cudaMemcpy(L.persist_op[oi], host.data(), ob, cudaMemcpyHostToDevice));

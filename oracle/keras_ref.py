@@ -1,13 +1,20 @@
 """ORACLE - TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's stage arithmetic.
 
-PARITY UNPINNED: the reference (ANRGUSC/DEFER) cannot be executed in this image - its arithmetic
-lives in un-vendored, un-pinned third-party wheels (TensorFlow ~1.14 + keras_applications 1.0.8,
-zfpy, lz4; call sites ``/root/reference/src/node.py:31,34,106``, ``src/dispatcher.py:49,57``,
-``test/test.py:14``) that are not installed and not installable offline, and none of its scripts
-compares a value (``test/test.py:34`` prints shapes).  This file therefore restates the *published*
-Keras layer semantics those call sites rely on, and is pinned only by (i) Keras' parameter counts
-for the three nets, (ii) hand-computed known-answer cases and a pure-Python-loop convolution
-(``tests/test_oracle.py``), (iii) agreement with an independent executor (``oracle/torch_cpu.py``).
+PARITY UNPINNED WITH RESPECT TO THE REFERENCE ITSELF: ANRGUSC/DEFER cannot be executed in this image - its
+arithmetic lives in un-vendored, un-pinned third-party wheels (TensorFlow ~1.14 + keras_applications 1.0.8, zfpy,
+lz4; call sites ``/root/reference/src/node.py:31,34,106``, ``src/dispatcher.py:49,57``, ``test/test.py:14``) that are
+not installed and not installable offline, and none of its scripts compares a value (``test/test.py:34`` prints
+shapes).  This file therefore restates the *published* Keras layer semantics those call sites rely on.
+
+What pins it instead (round 2): an implementation we did not write.  ``tests/test_oracle_pin.py`` transplants the
+seeded Keras-layout weights into ``torchvision.models.vgg16`` (arithmetically the Keras VGG16, 138 357 544 parameters)
+and into ``torchvision.models.resnet50`` with the stride moved from the 3x3 to the first 1x1 convolution, conv biases
+folded into the BatchNorm means and eps = 1e-3 (exactly the deltas between torchvision's v1.5 and keras_applications'
+``resnet50.py``); this oracle and the model zoo's graph JSON must reproduce torchvision's class probabilities to 1e-9
+(fp64) / 1e-5 (fp32), and an intermediate tensor (end of conv3_x) to 1e-9.  That removes the failure mode where the
+builder's graph and the builder's oracle share a topology mistake.  Further pins: Keras' parameter counts for the three
+nets, hand-computed known-answer cases and a pure-Python-loop convolution (``tests/test_oracle.py``), agreement with an
+independent executor (``oracle/torch_cpu.py``), committed golden vectors (``tests/golden/``).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference legs may
 import this module.  The product (``defer_b200``) never does.
