@@ -68,7 +68,7 @@ def parse_args():
 
 
 # engine defaults (measured on B200, profiles/README.md round 2): G queue items per launch, lanes per stage
-DEFAULT_COALESCE = {"resnet50": 16, "resnet152": 16, "vgg16": 8}
+DEFAULT_COALESCE = {"resnet50": 32, "resnet152": 16, "vgg16": 8}
 DEFAULT_DEPTH = 4
 
 

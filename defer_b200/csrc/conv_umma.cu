@@ -1258,7 +1258,7 @@ conv_mega_kernel(const MegaOp* __restrict__ ops, int n_ops, int stages, int use_
 constexpr int STREAM_EPI_WARPS = 8;
 constexpr int STREAM_THREADS = 96 + 32 * STREAM_EPI_WARPS;   // 352
 constexpr int STREAM_CTL_BYTES = 512;
-constexpr int STREAM_MAX_UNITS = 4;
+constexpr int STREAM_MAX_UNITS = 6;
 
 template <int NPLANES, int BN>
 struct StreamSmem {
@@ -1285,9 +1285,9 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };               // [8, 16)
   auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
-  auto ready_bar = [&](int u) { return bar_base + 8u * (20 + u); };              // unit holds the residual / may be written
-  auto done_bar = [&](int u) { return bar_base + 8u * (24 + u); };               // unit holds the finished chunk
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, U) + 8 * 28);
+  auto ready_bar = [&](int u) { return bar_base + 8u * (20 + u); };              // [20, 26) unit holds the residual / may be written
+  auto done_bar = [&](int u) { return bar_base + 8u * (26 + u); };               // [26, 32) unit holds the finished chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, U) + 8 * 32);
   const uint32_t unit_base = smem_base + SS::unit_off(STAGES);
   uint8_t* unit_ptr = smem + SS::unit_off(STAGES);
 
@@ -2546,11 +2546,18 @@ static int launch_stream_t(const void* dev_op, int n_tiles, int k_blocks, cudaSt
   if (!sms) DEFER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // shared-memory split: K-heavy tiles want every byte in the operand ring (fill rate = bytes in flight / ~2 us),
   // output-heavy tiles (a few k-blocks each) want several staging units so residual fetch, math and store overlap
-  int units = k_blocks >= env_int("DEFER_STREAM_KHEAVY", 6) ? 1 : (BN == 64 ? 4 : 3);
+  const bool kheavy = k_blocks >= env_int("DEFER_STREAM_KHEAVY", 6);
+  // one k-block per tile (K = 64): the ring needs a single stage per tile in flight, everything else goes to staging
+  // units so 3-4 residual chunks are prefetched (measured: 34 -> 29 us on the 56x56 64->256 convs at batch 16)
+  int units = kheavy ? 1 : (k_blocks == 1 ? (BN == 64 ? 5 : 4) : env_int("DEFER_STREAM_LIGHT_UNITS", BN == 64 ? 4 : 3));
   units = env_int("DEFER_STREAM_UNITS", units);
   if (units < 1) units = 1;
   if (units > STREAM_MAX_UNITS) units = STREAM_MAX_UNITS;
   int stages = (SMEM_CAP - STREAM_CTL_BYTES - 1024 - units * SS::UNIT) / L::STAGE;
+  if (!kheavy) {
+    const int cap = env_int("DEFER_STREAM_LIGHT_STAGES", 0);
+    if (cap > 0 && stages > cap) stages = cap;
+  }
   stages = env_int("DEFER_STREAM_STAGES", stages);
   if (stages > 8) stages = 8;
   while (stages > 1 && SS::total(stages, units) > SMEM_CAP) --stages;
