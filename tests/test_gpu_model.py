@@ -64,7 +64,8 @@ def test_megakernel_and_per_op_paths_agree_bitwise(resnet50, x224, monkeypatch):
             outs[mega] = r.predict(x224)
             n_kernels = r.num_kernels()
             assert ("megakernel group" in r.describe()) == (mega == "1")
-            assert n_kernels == (7 if mega == "1" else 58)
+            # per-op: 53 convs (the RGB stem is ONE fused kernel since round 2) + max-pool + GAP + dense + softmax
+            assert n_kernels == (6 if mega == "1" else 57), n_kernels
         finally:
             r.close()
     ref = _oracle(resnet50, x224)
@@ -306,3 +307,21 @@ def test_batch8_stream_kernel_vs_oracle_and_round1_executor(resnet50, monkeypatc
     for i in range(8):
         assert _rel(outs["1"][i], ref[i]) <= 1e-3, i
     assert _rel(outs["1"], outs["0"]) <= 1e-4
+
+
+def test_balanced_cuts_pipeline_on_gpu(resnet50, x224):
+    """SURVEY 8f rank 1 on the GPU: cut layers chosen by defer_b200.autocut from per-op times MEASURED on the device give a
+    legal pipeline with the same answer as the reference cut list (bitwise) and the oracle (<= 1e-3)."""
+    from defer_b200 import autocut
+    probe = StageRunner.from_model(resnet50, device=0, dtype="float32", max_batch=1, depth=1)
+    try:
+        op_us = [max(1.0, probe.time_op(i, iters=5, flush_l2=False)) for i in range(len(probe.plan.ops))]
+    finally:
+        probe.close()
+    cuts, stage_us = autocut.balanced_cuts(resnet50, 4, op_costs=op_us)
+    assert len(cuts) == 3 and len(stage_us) == 4
+    assert max(stage_us) <= 0.5 * sum(stage_us)          # no stage holds more than half of the measured work
+    outs = _pipeline_on_one_gpu(resnet50, cuts, x224, "float32", depth=2, n_items=3)
+    ref_cuts = _pipeline_on_one_gpu(resnet50, applications.default_cuts(resnet50, 4), x224, "float32", depth=2, n_items=2)
+    assert _rel(outs[0], _oracle(resnet50, x224)) <= 1e-3
+    assert np.array_equal(outs[0], ref_cuts[0])
