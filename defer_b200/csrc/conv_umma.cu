@@ -203,6 +203,16 @@ __device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint4 lds4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -505,8 +515,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
       constexpr int HALVES = BN / 64;
       constexpr int REGION = BM * 128;             // one (plane, half) tile: 128 rows x 128 B
       const int sw = r & 7;
-      uint8_t* stg_row = smem + r * 128;
-      const uint8_t* res_row = smem + res_off + r * 128;
+      const uint32_t stg_row = smem_base + r * 128;              // shared-space addresses: explicit LDS / STS, no generic path
+      const uint32_t res_row = smem_base + res_off + r * 128;
       const bool has_res = p.res != nullptr;
       const bool relu = p.flags & DEFER_FLAG_RELU;
       if (has_res) mbar_wait(res_full_bar, 0, p.error_flag, 4);
@@ -536,7 +546,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int ch = (chb + q) ^ sw;
-            const uint4 rh4 = *reinterpret_cast<const uint4*>(res_row + half * REGION + ch * 16);
+            const uint4 rh4 = lds4(res_row + half * REGION + ch * 16);
             const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -544,7 +554,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
               acc[q * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u);
             }
             if (NPLANES == 2) {
-              const uint4 rl4 = *reinterpret_cast<const uint4*>(res_row + (HALVES + half) * REGION + ch * 16);
+              const uint4 rl4 = lds4(res_row + (HALVES + half) * REGION + ch * 16);
               const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -572,8 +582,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
             }
           }
           const int ch = (chb + q) ^ sw;
-          *reinterpret_cast<uint4*>(stg_row + half * REGION + ch * 16) = h;
-          if (NPLANES == 2) *reinterpret_cast<uint4*>(stg_row + (HALVES + half) * REGION + ch * 16) = l;
+          sts4(stg_row + half * REGION + ch * 16, h.x, h.y, h.z, h.w);
+          if (NPLANES == 2) sts4(stg_row + (HALVES + half) * REGION + ch * 16, l.x, l.y, l.z, l.w);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
@@ -1289,7 +1299,6 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
   auto done_bar = [&](int u) { return bar_base + 8u * (26 + u); };               // [26, 32) unit holds the finished chunk
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, U) + 8 * 32);
   const uint32_t unit_base = smem_base + SS::unit_off(STAGES);
-  uint8_t* unit_ptr = smem + SS::unit_off(STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1520,7 +1529,7 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
         const int col0 = c * 64 + chalf * 32;        // first accumulator column of this warp's 32
         const int chn = c_base + col0;               // first output channel
         const int u = (int)(j % (uint32_t)U);
-        uint8_t* stg = unit_ptr + u * SS::UNIT + r * 128;
+        const uint32_t stg = unit_base + u * SS::UNIT + r * 128;     // shared-space address of this thread's staging row
         if (!direct) mbar_wait(ready_bar(u), (j / (uint32_t)U) & 1u, error_flag, 26);   // residual landed / unit free
         uint32_t v[32];
         tmem_ld32(taddr_row + col0, v);               // warp-collective
@@ -1556,7 +1565,7 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int ch16 = ((chalf * 4) + q) ^ sw;
-              const uint4 rh4 = *reinterpret_cast<const uint4*>(stg + ch16 * 16);
+              const uint4 rh4 = lds4(stg + ch16 * 16);
               const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rh4);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -1564,7 +1573,7 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
                 acc[q * 8 + 2 * t + 1] += __uint_as_float(hw[t] & 0xffff0000u);
               }
               if (NPLANES == 2) {
-                const uint4 rl4 = *reinterpret_cast<const uint4*>(stg + BM * 128 + ch16 * 16);
+                const uint4 rl4 = lds4(stg + BM * 128 + ch16 * 16);
                 const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl4);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -1621,8 +1630,8 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
             }
           } else {
             const int ch16 = ((chalf * 4) + q) ^ sw;
-            *reinterpret_cast<uint4*>(stg + ch16 * 16) = h;
-            if (NPLANES == 2) *reinterpret_cast<uint4*>(stg + BM * 128 + ch16 * 16) = l;
+            sts4(stg + ch16 * 16, h.x, h.y, h.z, h.w);
+            if (NPLANES == 2) sts4(stg + BM * 128 + ch16 * 16, l.x, l.y, l.z, l.w);
           }
         }
         if (!direct) {
@@ -1698,7 +1707,6 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
   auto in_empty_bar = [&](int b) { return bar_base + 8u * (26 + b); };           // builders are done with them
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SS::ctl_off(STAGES, in_bytes) + 8 * 28);
   const uint32_t unit_base = smem_base + SS::unit_off(STAGES);
-  uint8_t* unit_ptr = smem + SS::unit_off(STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1738,6 +1746,13 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // optional phase trace (DEFER_STEM_TRACE=<file>): CTA 0, first 8 tiles, 64 slots each: 0 producer issued the input rows,
+  // 1 builders saw them, 2 MMA got the accumulator, 3 MMA issued the tile, 4 epilogue saw the accumulator, 5 epilogue done,
+  // 6 store issued, 8 + kb builder finished k-block kb, 16 + kb MMA saw k-block kb complete
+  long long* trace = (p.trace && rank == 0) ? p.trace : nullptr;
+  auto stamp = [&](uint32_t tile_seq, int slot) {
+    if (trace && tile_seq < 8 && slot < 64) trace[tile_seq * 64 + slot] = (long long)gtimer();
+  };
   // input rows a tile needs: pixels [p0, p0 + 128) of image nb cover output rows oh0..oh1
   auto tile_rows = [&](int tile, int& nb, int& oh0, int& ih_lo, int& n_rows) {
     const int p0 = tile * BM;
@@ -1770,6 +1785,7 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
         const float* src = op.stem_x + ((size_t)nb * H + ih_lo) * row_len;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_base + SS::in_off(STAGES) + ib * in_bytes), "l"(src), "r"(bytes), "r"(in_full_bar(ib)) : "memory");
+        stamp(it, 0);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 32);
           const uint32_t b_dst = smem_base + stage * L::STAGE + NPLANES * L::A_PLANE;
@@ -1791,11 +1807,13 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
       for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
         const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(buf), aphase ^ 1, error_flag, 33);
+        stamp(it, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
         uint32_t accum = 0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase, error_flag, 34);
+          stamp(it, 16 + kb);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * L::STAGE;
           const uint32_t b_addr = a_addr + NPLANES * L::A_PLANE;
@@ -1816,6 +1834,7 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(buf));
+        stamp(it, 3);
       }
     }
     __syncwarp();
@@ -1833,6 +1852,7 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
         tma_store_4d(&op.tmy[0], src, 0, tile * BM, 0, 0);
         if (NPLANES == 2) tma_store_4d(&op.tmy[1], src + BM * 128, 0, tile * BM, 0, 0);
         bulk_commit();
+        stamp(it, 6);
         if (tile + csize < n_tiles) {
           // unit u ^ 1 (tile it + 1) is already released; unit u is needed again by tile it + 2: its store (this one)
           // must have finished reading - checked one iteration later, when only the newest group may still be pending
@@ -1857,10 +1877,11 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
     for (int tile = rank; tile < n_tiles; tile += csize, ++it) {
       const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(buf), aphase, error_flag, 36);
+      if (threadIdx.x == 96) stamp(it, 4);
       tc_fence_after();
       mbar_wait(ready_bar(buf), aphase, error_flag, 37);       // staging unit `buf` is free (its previous store has read it)
       const uint32_t taddr_row = tmem_base + buf * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-      uint8_t* stg = unit_ptr + buf * SS::UNIT + r * 128;
+      const uint32_t stg = unit_base + buf * SS::UNIT + r * 128;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int col0 = half * 32;
@@ -1906,13 +1927,14 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
             else hp[t] = pack_bf16x2(acc[q * 8 + 2 * t], acc[q * 8 + 2 * t + 1]);
           }
           const int ch16 = ((half * 4) + q) ^ sw;
-          *reinterpret_cast<uint4*>(stg + ch16 * 16) = h;
-          if (NPLANES == 2) *reinterpret_cast<uint4*>(stg + BM * 128 + ch16 * 16) = l;
+          sts4(stg + ch16 * 16, h.x, h.y, h.z, h.w);
+          if (NPLANES == 2) sts4(stg + BM * 128 + ch16 * 16, l.x, l.y, l.z, l.w);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(done_bar(buf));
+      if (threadIdx.x == 96) stamp(it, 5);
     }
   } else {
     // =================================================================== A builders (warps 7..14): two threads per tile row
@@ -1937,11 +1959,13 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
         if (ih >= ih_lo && ih < ih_lo + n_rows) rowmask |= 1u << a;
       }
       const bool colfast = col0 >= 0 && col0 + run <= row_len;         // no left / right padding inside this patch
-      const float* rows = reinterpret_cast<const float*>(smem + SS::in_off(STAGES) + ib * in_bytes) + (ih0 - ih_lo) * row_len + col0;
+      // shared-space byte address of the patch's first element (may point before the buffer: only valid elements are read)
+      const int rows = (int)(smem_base + SS::in_off(STAGES) + ib * in_bytes) + ((ih0 - ih_lo) * row_len + col0) * 4;
       mbar_wait(in_full_bar(ib), iph, error_flag, 38);
+      if (bt == 0) stamp(it, 1);
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1, error_flag, 39);
-        uint8_t* a_row = smem + stage * L::STAGE + r * 128;
+        const uint32_t a_row = smem_base + stage * L::STAGE + r * 128;
         int k = kb * BK + g0 * 8;
         int a = k / run, jj = k - a * run;
 #pragma unroll
@@ -1951,7 +1975,7 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
           for (int j = 0; j < 8; ++j) {
             float val = 0.f;
             if ((rowmask >> a) & 1u) {
-              if (colfast || (col0 + jj >= 0 && col0 + jj < row_len)) val = rows[a * row_len + jj];
+              if (colfast || (col0 + jj >= 0 && col0 + jj < row_len)) val = lds_f32((uint32_t)(rows + (a * row_len + jj) * 4));
             }
             v[j] = val;
             if (++jj == run) { jj = 0; ++a; }
@@ -1963,20 +1987,21 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
             split_bf16x2(v[2], v[3], hv.y, lv.y);
             split_bf16x2(v[4], v[5], hv.z, lv.z);
             split_bf16x2(v[6], v[7], hv.w, lv.w);
-            *reinterpret_cast<uint4*>(a_row + ch16 * 16) = hv;
-            *reinterpret_cast<uint4*>(a_row + L::A_PLANE + ch16 * 16) = lv;
+            sts4(a_row + ch16 * 16, hv.x, hv.y, hv.z, hv.w);
+            sts4(a_row + L::A_PLANE + ch16 * 16, lv.x, lv.y, lv.z, lv.w);
           } else {
             uint4 hv;
             hv.x = pack_bf16x2(v[0], v[1]);
             hv.y = pack_bf16x2(v[2], v[3]);
             hv.z = pack_bf16x2(v[4], v[5]);
             hv.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(a_row + ch16 * 16) = hv;
+            sts4(a_row + ch16 * 16, hv.x, hv.y, hv.z, hv.w);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
+        if (bt == 0) stamp(it, 8 + kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       __syncwarp();
@@ -2350,7 +2375,25 @@ void umma_conv_unbind(UmmaConvLaneArgs* a) {
 // with %globaltimer; written when a stage is destroyed; summarised by tools/timeline_stats.py.
 constexpr int TIMELINE_CAP = 1 << 19;
 static long long* g_timeline = nullptr;
+static long long* g_stem_trace = nullptr;   // DEFER_STEM_TRACE: phase stamps of conv_stem_kernel's CTA 0 (debug)
 void umma_timeline_dump() {
+  if (g_stem_trace && getenv("DEFER_STEM_TRACE")) {
+    long long hb[8 * 64];
+    if (cudaMemcpy(hb, g_stem_trace, sizeof hb, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      FILE* f = fopen(getenv("DEFER_STEM_TRACE"), "a");
+      if (f) {
+        fprintf(f, "# conv_stem_kernel, CTA 0, ns since the first stamp\n");
+        for (int i = 0; i < 8; ++i) {
+          if (!hb[i * 64]) continue;
+          fprintf(f, "tile %d:", i);
+          for (int j = 0; j < 64; ++j)
+            if (hb[i * 64 + j]) fprintf(f, " %d=%lld", j, hb[i * 64 + j] - hb[0]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
+  }
   const char* path = getenv("DEFER_TIMELINE");
   if (!g_timeline || !path) return;
   std::vector<long long> h(8 + (size_t)TIMELINE_CAP * 8);
@@ -2612,6 +2655,11 @@ void umma_mega_set_stem(void* host_op, const float* x, int h, int w, int cin, in
   op->stem_kh = kh; op->stem_kw = kw; op->stem_sh = sh; op->stem_sw = sw;
   op->stem_pad_t = pad_t; op->stem_pad_l = pad_l;
   op->stem_K = kh * kw * cin;
+  if (getenv("DEFER_STEM_TRACE") && !g_stem_trace) {
+    if (cudaMalloc((void**)&g_stem_trace, 8 * 64 * sizeof(long long)) == cudaSuccess) cudaMemset(g_stem_trace, 0, 8 * 64 * sizeof(long long));
+    else g_stem_trace = nullptr;
+  }
+  if (g_stem_trace) op->p.trace = g_stem_trace;
 }
 
 template <int NPLANES>
