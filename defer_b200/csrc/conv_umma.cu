@@ -1281,7 +1281,7 @@ struct StreamSmem {
 
 template <int NPLANES, int BN>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
-conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* error_flag) {
+conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int pdl, int* error_flag) {
   using L = SmemLayout<NPLANES, BN>;
   using SS = StreamSmem<NPLANES, BN>;
   constexpr int CH = BN / 64;                      // 64-column chunks per tile
@@ -1333,6 +1333,13 @@ conv_stream_kernel(const MegaOp* __restrict__ opp, int stages, int units, int* e
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (pdl) {
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, reading the op descriptor) overlapped
+    // the tail of the previous kernel of this lane; its outputs are visible only after this wait.  Our own dependents may
+    // start their prologue as soon as SMs free up.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   // optional phase trace (DEFER_UMMA_TRACE through defer_k_conv): CTA 0 stamps %globaltimer at role milestones of its
   // first 8 tiles - 64 slots per tile: 0 producer starts the tile, 1 producer issued its last k-block, 2 MMA got the
@@ -1687,7 +1694,7 @@ struct StemSmem {
 
 template <int NPLANES>
 __global__ void __launch_bounds__(STEM_THREADS, 1)
-conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int max_rows, int* error_flag) {
+conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int pdl, int* error_flag) {
   constexpr int BN = 64;
   using L = SmemLayout<NPLANES, BN>;
   using SS = StemSmem<NPLANES>;
@@ -1745,6 +1752,10 @@ conv_stem_kernel(const MegaOp* __restrict__ opp, int stages, int in_bytes, int m
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   // optional phase trace (DEFER_STEM_TRACE=<file>): CTA 0, first 8 tiles, 64 slots each: 0 producer issued the input rows,
   // 1 builders saw them, 2 MMA got the accumulator, 3 MMA issued the tile, 4 epilogue saw the accumulator, 5 epilogue done,
@@ -2617,8 +2628,24 @@ static int launch_stream_t(const void* dev_op, int n_tiles, int k_blocks, cudaSt
     grid = (n_tiles + rounds - 1) / rounds;
   }
   int* err = nullptr;
+  static const int pdl = env_int("DEFER_PDL", 0);
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(STREAM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SS::total(stages, units);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DEFER_CUDA(cudaLaunchKernelEx(&cfg, conv_stream_kernel<NPLANES, BN>, reinterpret_cast<const MegaOp*>(dev_op), stages, units, 1, err));
+    return DEFER_OK;
+  }
   conv_stream_kernel<NPLANES, BN><<<grid, STREAM_THREADS, SS::total(stages, units), st>>>(reinterpret_cast<const MegaOp*>(dev_op),
-                                                                                         stages, units, err);
+                                                                                         stages, units, 0, err);
   DEFER_CUDA(cudaGetLastError());
   return DEFER_OK;
 }
@@ -2687,6 +2714,22 @@ static int launch_stem_t(const void* dev_op, int n_tiles, int in_bytes, cudaStre
   const int rounds = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + rounds - 1) / rounds;
   int* err = nullptr;
+  static const int pdl = env_int("DEFER_PDL", 0);
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(STEM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SS::total(stages, in_bytes);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DEFER_CUDA(cudaLaunchKernelEx(&cfg, conv_stem_kernel<NPLANES>, reinterpret_cast<const MegaOp*>(dev_op), stages, in_bytes, 1, err));
+    return DEFER_OK;
+  }
   conv_stem_kernel<NPLANES><<<grid, STEM_THREADS, SS::total(stages, in_bytes), st>>>(reinterpret_cast<const MegaOp*>(dev_op), stages,
                                                                                    in_bytes, 0, err);
   DEFER_CUDA(cudaGetLastError());
