@@ -66,6 +66,7 @@ PROTOTYPES = {
     "defer_stage_finalize": (_i, [_vp]),
     "defer_stage_submit": (_i, [_vp, _u64, _vp, _u64]),
     "defer_stage_submit_part": (_i, [_vp, _u64, _i, _i, _vp, _u64]),
+    "defer_stage_submit_parts": (_i, [_vp, _u64, _i, _i, _i, C.POINTER(_vp), _u64]),
     "defer_stage_step": (_i, [_vp, _u64]),
     "defer_stage_result": (_i, [_vp, _u64, _vp, _u64]),
     "defer_stage_predict": (_i, [_vp, _vp, _u64, _vp, _u64]),

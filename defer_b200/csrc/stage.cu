@@ -1030,6 +1030,27 @@ int defer_stage_submit_part(defer_stage_t s, uint64_t seq, int index, int count,
   return DEFER_OK;
 }
 
+int defer_stage_submit_parts(defer_stage_t s, uint64_t seq, int first_index, int n_items, int samples_per_item,
+                             const void* const* host_ptrs, uint64_t nbytes_per_item) {
+  DEFER_CHECK(s && host_ptrs && n_items >= 1 && samples_per_item >= 1, "submit_parts: bad arguments");
+  DEFER_CHECK(s->cfg.is_first, "submit_parts: only the first stage takes host input");
+  const Buf& b = s->bufs[s->cfg.input_buf];
+  const size_t sample = b.bytes / (size_t)s->cfg.batch;
+  DEFER_CHECK(first_index >= 0 && first_index + n_items * samples_per_item <= s->cfg.batch,
+              "submit_parts: samples [%d, %d) outside the microbatch of %d", first_index, first_index + n_items * samples_per_item,
+              s->cfg.batch);
+  DEFER_CHECK(nbytes_per_item == sample * (size_t)samples_per_item, "submit_parts: items are %llu bytes, %d sample(s) are %zu",
+              (unsigned long long)nbytes_per_item, samples_per_item, sample * (size_t)samples_per_item);
+  DEFER_TRY(set_device(s));
+  Lane& L = s->lanes[seq % s->cfg.depth];
+  uint8_t* dst = (uint8_t*)L.buf[s->cfg.input_buf] + sample * (size_t)first_index;
+  for (int i = 0; i < n_items; ++i) {
+    DEFER_CHECK(host_ptrs[i], "submit_parts: item %d is null", i);
+    DEFER_CUDA(cudaMemcpyAsync(dst + (size_t)i * nbytes_per_item, host_ptrs[i], nbytes_per_item, cudaMemcpyHostToDevice, L.stream));
+  }
+  return DEFER_OK;
+}
+
 int defer_stage_step(defer_stage_t s, uint64_t seq) {
   DEFER_CHECK(s, "step: null");
   DEFER_CHECK(s->finalized, "step: call defer_stage_finalize first");

@@ -124,6 +124,12 @@ class DEFER:
         first = self.stages[0] if self.stages else self.dist.local_runner()
         G, B = self.coalesce, self.batch or 1
         hold, nh = self._hold, len(self._hold)
+        get_nowait = input.get_nowait
+        submit_items = first.submit_items if hasattr(first, "submit_items") else None
+        if submit_items is None:             # duck-typed stages (tests): fall back to one call per item
+            def submit_items(seq, group):
+                for i, x in enumerate(group):
+                    first.submit_part(seq, i * B, x)
         try:
             while not self._stop.is_set():
                 try:
@@ -136,20 +142,26 @@ class DEFER:
                 seq = self._submitted
                 n = 0
                 deadline = None
+                group = []
+                in_shape = None
                 while True:
-                    x = np.asarray(model_input)
-                    if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+                    x = model_input
+                    if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags["C_CONTIGUOUS"]):
                         x = np.ascontiguousarray(x, dtype=np.float32)
                     if x.shape[0] != B:
                         raise ValueError(f"queue item has batch {x.shape[0]}, DEFER was built for batch {B}")
+                    if in_shape is None:
+                        in_shape = x.shape
+                    elif x.shape != in_shape:
+                        raise ValueError(f"queue items of one group differ in shape: {x.shape} vs {in_shape}")
                     hold[self.items_submitted % nh] = x      # keep alive until the DMA has certainly happened
                     self.items_submitted += 1
-                    first.submit_part(seq, n * B, x)
+                    group.append(x)
                     n += 1
                     if n == G:
                         break
                     try:                                     # coalesce whatever is already waiting ...
-                        model_input = input.get_nowait()
+                        model_input = get_nowait()
                     except queue.Empty:                      # ... or arrives within the linger window
                         now = time.perf_counter()
                         if deadline is None:
@@ -160,6 +172,7 @@ class DEFER:
                             model_input = input.get(timeout=deadline - now)
                         except queue.Empty:
                             break
+                submit_items(seq, group)                     # one C call: a cudaMemcpyAsync per item on the lane's stream
                 self._group_n[seq % len(self._group_n)] = n
                 if self.dist is not None:
                     first.step(seq)

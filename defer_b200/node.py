@@ -65,6 +65,7 @@ class StageRunner:
         self.handle = C.c_void_p()
         self._pinned: Dict[int, tuple] = {}
         self._marks: Dict[int, int] = {}
+        self._ptr_arrays: Dict[int, object] = {}
         self._streams = 0
         if not (is_first and is_last):
             used = _STREAMS_PER_DEVICE.get(self.device, 0)
@@ -156,6 +157,18 @@ class StageRunner:
         if tuple(x.shape[1:]) != self.in_shape[1:]:
             raise ValueError(f"{self.name}: item shape {tuple(x.shape)} does not match stage input {self.in_shape}")
         A.check(self.lib.defer_stage_submit_part(self.handle, seq, index, x.shape[0], x.ctypes.data, x.nbytes))
+
+    def submit_items(self, seq: int, items) -> None:
+        """Coalesced ingress, one C call per group: ``items`` are C-contiguous float32 arrays of identical shape
+        ``(k,) + input_shape[1:]``; item i lands in samples ``[i*k, (i+1)*k)`` of microbatch ``seq``."""
+        n = len(items)
+        ptrs = self._ptr_arrays.get(n)
+        if ptrs is None:
+            ptrs = self._ptr_arrays[n] = (C.c_void_p * n)()
+        for i, x in enumerate(items):
+            ptrs[i] = x.__array_interface__["data"][0]
+        x0 = items[0]
+        A.check(self.lib.defer_stage_submit_parts(self.handle, seq, 0, n, x0.shape[0], ptrs, x0.nbytes))
 
     def step(self, seq: int) -> None:
         A.check(self.lib.defer_stage_step(self.handle, seq))

@@ -153,6 +153,11 @@ DEFER_API int defer_stage_submit(defer_stage_t s, uint64_t seq, const void* host
  * built with batch = G x item-batch runs G in-flight items per launch.  Copies `count` consecutive samples of
  * microbatch `seq`, starting at sample `index`, from host memory (nbytes = count x bytes of one sample). */
 DEFER_API int defer_stage_submit_part(defer_stage_t s, uint64_t seq, int index, int count, const void* host_in, uint64_t nbytes);
+/* The same for a run of queue items in ONE call (the dispatcher's feeder gathers the items of a group, then ships them):
+ * item i (samples_per_item samples, nbytes_per_item bytes at host_ptrs[i]) goes to samples
+ * [first_index + i * samples_per_item, ...). */
+DEFER_API int defer_stage_submit_parts(defer_stage_t s, uint64_t seq, int first_index, int n_items, int samples_per_item,
+                             const void* const* host_ptrs, uint64_t nbytes_per_item);
 /* Enqueue microbatch `seq` on lane seq % depth: wait-input -> kernel chain -> hop -> flags. Async. */
 DEFER_API int defer_stage_step(defer_stage_t s, uint64_t seq);
 /* Last stage only: block until microbatch `seq` is complete and copy its fp32 output to host. */

@@ -17,13 +17,13 @@ WANT = {
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "tensor_pct": "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+    "tensor_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "regs": "launch__registers_per_thread",
     "grid": "launch__grid_size",
     "smem_dyn": "launch__shared_mem_per_block_dynamic",
 }
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3,
-         "msecond": 1e3}
+         "msecond": 1e3, "Kbyte/block": 1e3, "byte/block": 1.0, "Mbyte/block": 1e6}
 
 
 def short(name: str) -> str:
