@@ -471,11 +471,97 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const void* __restrict__ x
   act_store4<FMT>(y, plane_out, pix * c + cg * 4, m);
 }
 
+// 8 channels per thread, 16-byte loads / stores per bf16 plane (the pool is a pure HBM stream: wide accesses halve the
+// instruction count of the 4-channel version).  max() is exact on bf16 values, so it is taken plane-wise on the decoded sums
+// exactly like the 4-channel kernel: decode hi + lo -> fp32, max, re-split.
+template <int FMT>
+__global__ void __launch_bounds__(256) maxpool8_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w,
+                                                       int c, int ph, int pw, int sh, int sw, int pad_t, int pad_l, int ho,
+                                                       int wo) {
+  const int c8 = c >> 3;
+  const size_t total = (size_t)n * ho * wo * c8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % c8);
+  const size_t pix = i / c8;
+  const int ow = (int)(pix % wo);
+  const size_t t2 = pix / wo;
+  const int oh = (int)(t2 % ho);
+  const int nb = (int)(t2 / ho);
+  const size_t plane_in = (size_t)n * h * w * c, plane_out = (size_t)n * ho * wo * c;
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int a = 0; a < ph; ++a) {
+    const int ih = oh * sh - pad_t + a;
+    for (int b = 0; b < pw; ++b) {
+      const int iw = ow * sw - pad_l + b;
+      float v[8];
+      if (ih >= 0 && ih < h && iw >= 0 && iw < w) {
+        const size_t o = (((size_t)nb * h + ih) * w + iw) * c + (size_t)cg * 8;
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(xp + o));
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          v[2 * t] = __uint_as_float(hw[t] << 16);
+          v[2 * t + 1] = __uint_as_float(hw[t] & 0xffff0000u);
+        }
+        if constexpr (FMT == FMT_BF16X2) {
+          const uint4 lv = __ldg(reinterpret_cast<const uint4*>(xp + plane_in + o));
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            v[2 * t] += __uint_as_float(lw[t] << 16);
+            v[2 * t + 1] += __uint_as_float(lw[t] & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;      // Keras' explicit ZeroPadding2D: padded taps read 0.0
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  }
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const size_t o = pix * c + (size_t)cg * 8;
+  uint4 hv, lv;
+  if constexpr (FMT == FMT_BF16X2) {
+    split_bf16x2(m[0], m[1], hv.x, lv.x);
+    split_bf16x2(m[2], m[3], hv.y, lv.y);
+    split_bf16x2(m[4], m[5], hv.z, lv.z);
+    split_bf16x2(m[6], m[7], hv.w, lv.w);
+    *reinterpret_cast<uint4*>(yp + o) = hv;
+    *reinterpret_cast<uint4*>(yp + plane_out + o) = lv;
+  } else {
+    hv.x = pack_bf16x2(m[0], m[1]);
+    hv.y = pack_bf16x2(m[2], m[3]);
+    hv.z = pack_bf16x2(m[4], m[5]);
+    hv.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(yp + o) = hv;
+  }
+}
+
 int launch_maxpool(int fmt, const void* x, void* y, int n, int h, int w, int c, int ph, int pw, int sh, int sw,
                    int pad_t, int pad_l, int ho, int wo, cudaStream_t st) {
   if (c % 4 != 0) {
     set_error("maxpool: channels %d not a multiple of 4", c);
     return DEFER_ERR_INVALID;
+  }
+  static const bool wide = getenv("DEFER_MAXPOOL8") == nullptr || atoi(getenv("DEFER_MAXPOOL8")) != 0;
+  if (wide && c % 8 == 0 && (fmt == FMT_BF16X2 || fmt == FMT_BF16)) {
+    const size_t total8 = (size_t)n * ho * wo * (c / 8);
+    const unsigned grid8 = (unsigned)((total8 + 255) / 256);
+    if (fmt == FMT_BF16X2) {
+      prefer_max_smem(maxpool8_kernel<FMT_BF16X2>);
+      maxpool8_kernel<FMT_BF16X2><<<grid8, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo);
+    } else {
+      prefer_max_smem(maxpool8_kernel<FMT_BF16>);
+      maxpool8_kernel<FMT_BF16><<<grid8, 256, 0, st>>>(x, y, n, h, w, c, ph, pw, sh, sw, pad_t, pad_l, ho, wo);
+    }
+    DEFER_CUDA(cudaGetLastError());
+    return DEFER_OK;
   }
   size_t total = (size_t)n * ho * wo * (c / 4);
   unsigned grid = (unsigned)((total + 255) / 256);
