@@ -205,7 +205,10 @@ DEFER_API int defer_host_unregister(void* ptr);
 /* Each runs ONE kernel on `stream` (cudaStream_t as void*, NULL = default) so it can be parity-
  * tested and ncu-profiled alone.  Activation tensors are in `fmt`; planes of BF16X2 are
  * [hi | lo], lo at element offset n*h*w*c. Weights: fp32 HWIO + fp32 scale/shift (may be NULL). */
-DEFER_API int defer_k_conv(int fmt, int backend /*1 SIMT, 2 tcgen05*/,
+/* backend: 1 SIMT FFMA | 2 tcgen05, one tile per CTA (conv_umma_kernel) | 3 round-1 persistent grid (conv_mega_kernel) |
+ *          4 / 5 streaming persistent kernel (conv_stream_kernel) with 64- / 128-wide N tiles |
+ *          6 / 7 the same with the per-thread (peer-memory capable) epilogue */
+DEFER_API int defer_k_conv(int fmt, int backend,
                  const void* x, int x_is_f32, const float* w_hwio, const float* scale, const float* shift,
                  const void* residual, void* y,
                  int n, int h, int w, int cin, int cout, int kh, int kw, int sh, int sw,
