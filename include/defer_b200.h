@@ -7,9 +7,11 @@
  * and the dispatcher feeds / drains the chain (src/dispatcher.py:85-105).  This library replaces
  * exactly that: a *stage* is a fused-op plan + weights resident in HBM on one B200; its forward
  * pass is hand-written sm_100a kernels captured in a CUDA graph per in-flight lane; the hop is a
- * store of the stage's last kernel straight into the next stage's input slot over NVLink (peer or
- * CUDA-IPC mapped) followed by a release flag - no host round trip, no codec (the reference codec
- * is lossless, src/node.py:76-79, so a raw copy is bit-equivalent).
+ * copy-engine transfer (or, optionally, the last kernel's own stores) of the stage output into the
+ * next stage's input slot over NVLink (peer or CUDA-IPC mapped) followed by a release flag - no host
+ * round trip, no codec (the reference codec is lossless, src/node.py:76-79, so a raw copy is
+ * bit-equivalent).  Queue items stay single samples; a stage built with batch = G x item-batch runs
+ * G in-flight items per launch (defer_stage_submit_part / _parts).
  *
  * Conventions: every entry point is extern "C", returns 0 on success and a negative defer_status
  * on failure; defer_last_error() gives a thread-local message.  No exception, torch type or C++
