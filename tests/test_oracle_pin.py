@@ -122,3 +122,46 @@ def test_resnet50_oracle_matches_stride_moved_torchvision():
     got32 = keras_ref.predict(m.to_json(), m.get_weights(), x, dtype=np.float32)
     assert keras_ref.rel_err(got32, want) <= 1e-5
     assert int(np.argmax(got32)) == int(np.argmax(want))
+
+
+@pytest.mark.timeout(900)
+def test_resnet152_oracle_matches_stride_moved_torchvision():
+    """Same pin for the `resnet_common` family (BASELINE config 5): torchvision's resnet152 with the stride moved to the
+    first 1x1 conv of each down-sampling block, conv biases folded into BN and eps = 1.001e-5 (keras_applications
+    `resnet_common.block1`), at a reduced 96x96 resolution to keep the CPU suite short."""
+    m = applications.ResNet152(input_shape=(96, 96, 3))
+    tv = tvm.resnet152(weights=None).double().eval()
+    assert m.count_params() == 60_419_944
+    _move_stride_to_first_conv(tv)
+
+    def load(conv, bn, name):
+        k, b = m.get_layer(name + "_conv").get_weights()
+        gamma, beta, mean, var = m.get_layer(name + "_bn").get_weights()
+        with torch.no_grad():
+            conv.weight.copy_(_conv_w(k))
+            bn.weight.copy_(_t(gamma))
+            bn.bias.copy_(_t(beta))
+            bn.running_mean.copy_(_t(mean.astype(np.float64) - b.astype(np.float64)))
+            bn.running_var.copy_(_t(var))
+        bn.eps = 1.001e-5
+
+    load(tv.conv1, tv.bn1, "conv1")
+    for si, layer in enumerate((tv.layer1, tv.layer2, tv.layer3, tv.layer4), start=2):
+        for bi, blk in enumerate(layer, start=1):
+            tag = f"conv{si}_block{bi}"
+            load(blk.conv1, blk.bn1, tag + "_1")
+            load(blk.conv2, blk.bn2, tag + "_2")
+            load(blk.conv3, blk.bn3, tag + "_3")
+            if blk.downsample is not None:
+                load(blk.downsample[0], blk.downsample[1], tag + "_0")
+    k, b = m.get_layer("probs").get_weights()
+    with torch.no_grad():
+        tv.fc.weight.copy_(_t(k.T))
+        tv.fc.bias.copy_(_t(b))
+    x = applications.synthetic_input(1, shape=(96, 96, 3), seed=23)
+    with torch.no_grad():
+        want = _softmax(tv(_t(np.transpose(x, (0, 3, 1, 2)))).numpy())
+    got64 = keras_ref.predict(m.to_json(), m.get_weights(), x, dtype=np.float64)
+    assert keras_ref.rel_err(got64, want) <= 1e-9
+    got32 = keras_ref.predict(m.to_json(), m.get_weights(), x, dtype=np.float32)
+    assert keras_ref.rel_err(got32, want) <= 2e-5
